@@ -1,0 +1,160 @@
+/* egom2p_b200 -- C ABI of the B200 (sm_100a) kernels behind the EgoM2P masked multimodal training step.
+ *
+ * Every entry point takes plain device pointers + sizes + a cudaStream_t (passed as void*), launches on
+ * that stream only, never synchronises the device, never allocates device memory, and returns 0 or a
+ * negative EGOM2P_ERR_* code (message via egom2p_last_error(), thread-local). No torch types cross this
+ * boundary. The reference is pure Python/PyTorch (no FFI of its own), so each group below names the
+ * reference code (path:line under the upstream repo) whose eager-op sequence it replaces; the Python
+ * binding a maintainer adds is a ctypes stub.
+ *
+ * Conventions: row-major; "rows" = tokens (batch*sequence flattened); bf16 = __nv_bfloat16 bits (uint16_t);
+ * masks are uint8 (torch.bool) with 1 = masked-out, as in the reference's input_mask / target_mask.
+ */
+#ifndef EGOM2P_B200_H_
+#define EGOM2P_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGOM2P_OK 0
+#define EGOM2P_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define EGOM2P_ERR_CUDA (-2)    /* CUDA runtime / driver error at launch */
+
+#define EGOM2P_MAX_MODS 8
+
+const char* egom2p_last_error(void);
+int egom2p_abi_version(void);
+/* Number of kernels this library has launched on behalf of the calling process (bench.py: gpu_launches). */
+int64_t egom2p_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Index plan + fused embedding gather.
+ * Replaces cat_encoder_tensors / forward_mask_encoder (egom2p/models/egom2p_model.py:251-283,344-396),
+ * cat_decoder_tensors / forward_mask_decoder / adapt_decoder_attention_mask (:285-342,398-481) and the
+ * adapter forwards (egom2p/models/encoder_embeddings.py:181-210,272-301; decoder_embeddings.py:337-370,455-487).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_mods;                          /* modalities in CONCAT order (encoder: mod_dict order; decoder: shuffled order) */
+  int32_t batch;                           /* B */
+  int32_t budget;                          /* num_encoder_tokens / num_decoder_tokens */
+  int32_t is_decoder;                      /* 0: encoder plan, 1: decoder plan (needs attn_cnt, ids) */
+  int32_t causal;                          /* decoder_causal_mask */
+  int32_t sep;                             /* decoder_sep_mask */
+  int32_t len[EGOM2P_MAX_MODS];            /* tokens per sample of each modality */
+  int32_t mod_id[EGOM2P_MAX_MODS];         /* modality_info[mod]['id'] (int16 range) */
+  const uint8_t* mask[EGOM2P_MAX_MODS];    /* (B, len) input_mask / target_mask */
+  const int32_t* attn_cnt[EGOM2P_MAX_MODS];/* (B, len) decoder_attention_mask, decoder only */
+  const int64_t* ids[EGOM2P_MAX_MODS];     /* (B, len) token ids, decoder only (target ids) */
+} egom2p_plan_desc;
+
+/* Stable partition of the concatenated mask (== argsort(mask + arange*1e-6)[:, :budget]).
+ * Outputs (device): keep_idx (B,budget) int32 concat index; keep_mod / keep_pos (B,budget) int32 modality slot and
+ * position inside it; pad (B,budget) uint8 (1 = pad slot); mod_mask (B,budget) int16 (-1 on pads);
+ * n_valid (B) int32. Decoder only: target_ids (B,budget) int64 (0 on pads); key_lo/key_hi (B,budget) int32 = the
+ * contiguous key range each decoder row may attend (empty range == every key masked). */
+int egom2p_index_plan(const egom2p_plan_desc* desc, int32_t* keep_idx, int32_t* keep_mod, int32_t* keep_pos,
+                      uint8_t* pad, int16_t* mod_mask, int32_t* n_valid, int64_t* target_ids, int32_t* key_lo,
+                      int32_t* key_hi, void* stream);
+
+typedef struct {
+  int32_t n_mods;
+  int32_t dim;
+  int32_t len[EGOM2P_MAX_MODS];
+  int32_t vocab[EGOM2P_MAX_MODS];
+  const int64_t* ids[EGOM2P_MAX_MODS];     /* (B, len) token ids (encoder) or NULL (decoder: mask token) */
+  const float* token_emb[EGOM2P_MAX_MODS]; /* (vocab, dim) fp32 or NULL */
+  const float* pos_emb[EGOM2P_MAX_MODS];   /* (len, dim) fp32 */
+  const float* mod_emb[EGOM2P_MAX_MODS];   /* (dim) fp32 */
+} egom2p_embed_desc;
+
+/* x0[r] = tok[r] + (pos_emb[p] + mod_emb)  and  emb[r] = pos_emb[p] + mod_emb  for kept slot r; pads -> 0.
+ * tok[r] = token_emb[ids] (encoder) or mask_token (decoder, mask_token != NULL). emb may be NULL. */
+int egom2p_embed_gather_fwd(const egom2p_embed_desc* desc, const float* mask_token, const int32_t* keep_mod,
+                            const int32_t* keep_pos, const uint8_t* pad, int64_t rows, int32_t budget, float* x0,
+                            float* emb, void* stream);
+/* Gradients of the above: d_token_emb[m][id] += dx0[r] (atomic scatter-add), d_mod_emb[m] += sum_r (dx0[r] + demb[r]),
+ * d_mask_token += sum_r dx0[r]; all accumulate into the given fp32 buffers (any may be NULL). demb may be NULL. */
+int egom2p_embed_gather_bwd(const egom2p_embed_desc* desc, const float* dx0, const float* demb, const int32_t* keep_mod,
+                            const int32_t* keep_pos, const uint8_t* pad, int64_t rows, int32_t budget,
+                            float* const* d_token_emb, float* const* d_mod_emb, float* d_mask_token, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3a) LayerNorm (no bias, eps) -- egom2p/models/egom2p_utils.py:118-133. fp32 in; bf16 and/or fp32 out.
+ * ------------------------------------------------------------------------------------------------ */
+int egom2p_layernorm_fwd(const float* x, const float* weight, int64_t rows, int32_t dim, float eps, uint16_t* y_bf16,
+                         float* y_f32, float* mean, float* rstd, void* stream);
+/* dx_out = dx_in (may be NULL) + LN'(dy); dy given as bf16 or fp32 (exactly one non-NULL); d_weight += sum_r dy*xhat.
+ * dx_bf16 (optional) receives a bf16 copy of dx_out. */
+int egom2p_layernorm_bwd(const uint16_t* dy_bf16, const float* dy_f32, const float* x, const float* weight,
+                         const float* mean, const float* rstd, const float* dx_in, int64_t rows, int32_t dim,
+                         float* dx_out, uint16_t* dx_bf16, float* d_weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3b) bf16 GEMM on tcgen05/TMEM fed by TMA -- every nn.Linear on the path (egom2p_utils.py:167-169,187,203,226-228,
+ * egom2p_model.py:722) and their dgrad / wgrad.  C[M,N] = op(A) * op(B)^T with fp32 accumulation:
+ *   a_mn = 0: A is (M,K) row-major (K contiguous);  a_mn = 1: A is stored (K,M) row-major (M contiguous)
+ *   b_mn = 0: B is (N,K) row-major (K contiguous);  b_mn = 1: B is stored (K,N) row-major (N contiguous)
+ * lda/ldb = row pitch in elements of the stored matrices. Epilogue: out = acc (+ bias[n]) (+ addend[m,n]);
+ * written as bf16 (c_bf16) and/or fp32 (c_f32); addend may alias c_f32.
+ * ------------------------------------------------------------------------------------------------ */
+int egom2p_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, int64_t lda, int64_t ldb,
+                     int32_t a_mn, int32_t b_mn, const float* bias, const float* addend, int64_t ld_add,
+                     uint16_t* c_bf16, float* c_f32, int64_t ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) Vocabulary head fused with softmax cross-entropy (egom2p/models/decoder_embeddings.py:489-500,
+ * egom2p_model.py:614-644): logits = Y W^T are produced tile-by-tile in TMEM and never written to HBM.
+ * ------------------------------------------------------------------------------------------------ */
+/* Pass 1: per (row, vocab tile) partial max / sum-exp and the target logit. part_* are (n_tiles, R) fp32 with
+ * n_tiles = ceil(V / 256); tgt_logit (R) fp32 must be zero-initialised. */
+int egom2p_ce_partials(const uint16_t* Y, const uint16_t* W, const int64_t* target, int32_t R, int32_t V, int32_t K,
+                       int64_t ldy, int64_t ldw, float* part_max, float* part_sum, float* tgt_logit, void* stream);
+/* Pass 2: lse[r] = logsumexp over tiles; loss_sum += sum_r (lse[r] - tgt_logit[r]) (one fp32, atomically). */
+int egom2p_ce_finalize(const float* part_max, const float* part_sum, const float* tgt_logit, int32_t R,
+                       int32_t n_tiles, float* lse, float* loss_sum, void* stream);
+/* Backward recompute: dlogits[r, v0:v0+Vc] = (exp(logit - lse[r]) - [v == target[r]]) * gscale[0] as bf16 (R, Vc),
+ * for the vocab chunk [v0, v0+Vc). gscale is a device scalar (upstream grad / R). */
+int egom2p_ce_dlogits(const uint16_t* Y, const uint16_t* W, const int64_t* target, const float* lse,
+                      const float* gscale, int32_t R, int32_t v0, int32_t Vc, int32_t K, int64_t ldy, int64_t ldw,
+                      uint16_t* dlogits, int64_t ldd, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Attention, head_dim 64, tcgen05/TMEM tiles fed by TMA, online softmax in fp32
+ * (egom2p/models/egom2p_utils.py:185-205 self, :222-244 cross). Q rows live at Q + (b*Mq + i)*ldq + h*64 (same for
+ * K/V with Nk, ldk/ldv; O with ldo), so packed qkv / kv projections are consumed in place. Each query row attends
+ * the contiguous key range [key_lo[b*Mq+i], key_hi[...]) of its sample (NULL: [0, Nk)). An empty range reproduces the
+ * reference's masked_fill(-finfo.max) behaviour: uniform attention over all Nk keys. lse (B,H,Mq) fp32 is saved
+ * for the backward pass.
+ * ------------------------------------------------------------------------------------------------ */
+int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, int32_t B, int32_t H, int32_t Mq, int32_t Nk,
+                    int64_t ldq, int64_t ldk, int64_t ldv, const int32_t* key_lo, const int32_t* key_hi, float scale,
+                    uint16_t* O, int64_t ldo, float* lse, void* stream);
+/* delta (B,H,Mq) fp32 is scratch. dQ/dK/dV use the same addressing as Q/K/V (ld*q, ld*k, ld*v). */
+int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, const uint16_t* O, const uint16_t* dO,
+                    const float* lse, int32_t B, int32_t H, int32_t Mq, int32_t Nk, int64_t ldq, int64_t ldk, int64_t ldv,
+                    int64_t ldo, const int32_t* key_lo, const int32_t* key_hi, float scale, float* delta, uint16_t* dQ,
+                    uint16_t* dK, uint16_t* dV, int64_t lddq, int64_t lddk, int64_t lddv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise helpers on the path.
+ * ------------------------------------------------------------------------------------------------ */
+/* g = silu(a) * b with ab = [a | b] (rows, 2*hidden) bf16 -> g (rows, hidden) bf16 (egom2p_utils.py:167-169). */
+int egom2p_swiglu_fwd(const uint16_t* ab, int64_t rows, int32_t hidden, uint16_t* g, void* stream);
+int egom2p_swiglu_bwd(const uint16_t* ab, const uint16_t* dg, int64_t rows, int32_t hidden, uint16_t* dab, void* stream);
+int egom2p_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
+/* out = a + b (fp32), optional bf16 copy. */
+int egom2p_add_f32(const float* a, const float* b, int64_t n, float* out, uint16_t* out_bf16, void* stream);
+/* Fused AdamW over one flat fp32 tensor (torch.optim.AdamW semantics; egom2p/utils/optim_factory.py:206-226),
+ * grad pre-scaled by *grad_scale (device scalar, e.g. the clip coefficient; NULL = 1). */
+int egom2p_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* grad_scale,
+                      void* stream);
+/* sumsq[0] += sum(x^2) (fp32 atomics) -- building block of clip_grad_norm_ (egom2p/utils/native_scaler.py:29-33). */
+int egom2p_sumsq_f32(const float* x, int64_t n, float* sumsq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOM2P_B200_H_ */
