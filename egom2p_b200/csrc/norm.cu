@@ -1,0 +1,190 @@
+// LayerNorm without bias (egom2p_utils.py:118-133), fp32 statistics. One warp per row, row held in registers,
+// 16-byte vector loads/stores. HBM-bound: fwd moves 4*D bytes in + 2*D (bf16) out per row.
+#include "common.cuh"
+
+namespace egom2p {
+
+constexpr int kLnMaxVec = 16;  // float4 per lane -> dim <= 2048
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     int64_t rows, int dim, float eps, uint16_t* __restrict__ yb,
+                                                     float* __restrict__ yf, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int D4 = dim >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + j * 32;
+    if (i < D4) {
+      v[j] = xr[i];
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+  }
+  const float mean = warp_sum(s) / dim;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + j * 32;
+    if (i < D4) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const float4* wr = reinterpret_cast<const float4*>(w);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + j * 32;
+    if (i < D4) {
+      const float4 g = __ldg(wr + i);
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * g.x;
+      o.y = (v[j].y - mean) * rstd * g.y;
+      o.z = (v[j].z - mean) * rstd * g.z;
+      o.w = (v[j].w - mean) * rstd * g.w;
+      if (yf) reinterpret_cast<float4*>(yf + row * dim)[i] = o;
+      if (yb) {
+        uint2 pk;
+        pk.x = pack_bf16(o.x, o.y);
+        pk.y = pack_bf16(o.z, o.w);
+        reinterpret_cast<uint2*>(yb + row * dim)[i] = pk;
+      }
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w ; dw += sum_rows dy * xhat.
+// Each warp walks rows [row0 + warp, ...) with stride 8 inside its CTA's row chunk and keeps per-lane dw partials.
+template <bool kDyBf16, int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
+                                                     const float* __restrict__ w, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const float* __restrict__ dx_in,
+                                                     int64_t rows, int dim, int rows_per_cta, float* __restrict__ dx_out,
+                                                     uint16_t* __restrict__ dx_bf16, float* __restrict__ dw) {
+  extern __shared__ float s_dw[];  // 8 warps x dim
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D4 = dim >> 2;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(r0 + (int64_t)rows_per_cta, rows);
+  float4 acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  for (int64_t row = r0 + warp; row < r1; row += 8) {
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + j * 32;
+      if (i < D4) {
+        const float4 xv = xr[i];
+        float4 d;
+        if (kDyBf16) {
+          const uint2 raw = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy_) + row * dim)[i];
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          d = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          d = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * dim)[i];
+        }
+        const float4 wv = __ldg(wr + i);
+        xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        acc[j].x += d.x * xh[j].x; acc[j].y += d.y * xh[j].y; acc[j].z += d.z * xh[j].z; acc[j].w += d.w * xh[j].w;
+        g[j] = make_float4(d.x * wv.x, d.y * wv.y, d.z * wv.z, d.w * wv.w);
+        s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+        s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+      }
+    }
+    const float m1 = warp_sum(s1) / dim, m2 = warp_sum(s2) / dim;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + j * 32;
+      if (i < D4) {
+        float4 o;
+        o.x = rs * (g[j].x - m1 - xh[j].x * m2);
+        o.y = rs * (g[j].y - m1 - xh[j].y * m2);
+        o.z = rs * (g[j].z - m1 - xh[j].z * m2);
+        o.w = rs * (g[j].w - m1 - xh[j].w * m2);
+        if (dx_in) {
+          const float4 r = reinterpret_cast<const float4*>(dx_in + row * dim)[i];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        reinterpret_cast<float4*>(dx_out + row * dim)[i] = o;
+        if (dx_bf16) {
+          uint2 pk;
+          pk.x = pack_bf16(o.x, o.y);
+          pk.y = pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(dx_bf16 + row * dim)[i] = pk;
+        }
+      }
+    }
+  }
+  if (!dw) return;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + j * 32;
+    if (i < D4) reinterpret_cast<float4*>(s_dw + warp * dim)[i] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) t += s_dw[wi * dim + c];
+    atomicAdd(dw + c, t);
+  }
+}
+
+}  // namespace egom2p
+
+extern "C" int egom2p_layernorm_fwd(const float* x, const float* weight, int64_t rows, int32_t dim, float eps,
+                                    uint16_t* y_bf16, float* y_f32, float* mean, float* rstd, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(x && weight && rows > 0, "layernorm_fwd: null input");
+  EGO_REQUIRE(dim % 4 == 0 && dim > 0 && dim <= kLnMaxVec * 128, "layernorm_fwd: dim %d unsupported (multiple of 4, <= %d)", dim, kLnMaxVec * 128);
+  EGO_REQUIRE(y_bf16 || y_f32, "layernorm_fwd: no output");
+  const int nv = (dim / 4 + 31) / 32;
+#define EGO_LN_FWD(NV) ln_fwd_kernel<NV><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, weight, rows, dim, eps, y_bf16, y_f32, mean, rstd)
+  if (nv <= 2) EGO_LN_FWD(2); else if (nv <= 3) EGO_LN_FWD(3); else if (nv <= 4) EGO_LN_FWD(4); else if (nv <= 6) EGO_LN_FWD(6);
+  else if (nv <= 8) EGO_LN_FWD(8); else EGO_LN_FWD(16);
+#undef EGO_LN_FWD
+  return check_launch("layernorm_fwd");
+}
+
+extern "C" int egom2p_layernorm_bwd(const uint16_t* dy_bf16, const float* dy_f32, const float* x, const float* weight,
+                                    const float* mean, const float* rstd, const float* dx_in, int64_t rows, int32_t dim,
+                                    float* dx_out, uint16_t* dx_bf16, float* d_weight, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_bwd: exactly one of dy_bf16 / dy_f32");
+  EGO_REQUIRE(x && weight && mean && rstd && dx_out && rows > 0, "layernorm_bwd: null argument");
+  EGO_REQUIRE(dim % 4 == 0 && dim > 0 && dim <= kLnMaxVec * 128, "layernorm_bwd: dim %d unsupported", dim);
+  const int rows_per_cta = 64;
+  const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+  const size_t smem = (size_t)8 * dim * sizeof(float);
+  const int nv = (dim / 4 + 31) / 32;
+#define EGO_LN_BWD(NV)                                                                                                  \
+  do {                                                                                                                  \
+    if (dy_bf16) {                                                                                                      \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<true, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      ln_bwd_kernel<true, NV><<<grid, 256, smem, (cudaStream_t)stream>>>(dy_bf16, x, weight, mean, rstd, dx_in, rows, dim, rows_per_cta, dx_out, dx_bf16, d_weight); \
+    } else {                                                                                                            \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<false, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      ln_bwd_kernel<false, NV><<<grid, 256, smem, (cudaStream_t)stream>>>(dy_f32, x, weight, mean, rstd, dx_in, rows, dim, rows_per_cta, dx_out, dx_bf16, d_weight); \
+    }                                                                                                                   \
+  } while (0)
+  if (nv <= 2) EGO_LN_BWD(2); else if (nv <= 3) EGO_LN_BWD(3); else if (nv <= 4) EGO_LN_BWD(4); else if (nv <= 6) EGO_LN_BWD(6);
+  else if (nv <= 8) EGO_LN_BWD(8); else EGO_LN_BWD(16);
+#undef EGO_LN_BWD
+  return check_launch("layernorm_bwd");
+}

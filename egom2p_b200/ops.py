@@ -1,0 +1,288 @@
+"""Tensor-level wrappers over the C ABI: torch owns the memory and the stream, the library launches kernels.
+
+Every function requires CUDA tensors and raises otherwise -- there is deliberately no CPU / eager fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"egom2p_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"egom2p_b200: {name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+# ----------------------------------------------------------------------------------------------- index plan
+class Plan:
+    """Outputs of egom2p_index_plan for one side (encoder or decoder)."""
+    __slots__ = ("keep_idx", "keep_mod", "keep_pos", "pad", "mod_mask", "n_valid", "target_ids", "key_lo", "key_hi",
+                 "B", "budget", "order")
+
+
+def index_plan(masks: Sequence[torch.Tensor], mod_ids: Sequence[int], budget: int, *, decoder: bool = False,
+               attn_cnt: Optional[Sequence[torch.Tensor]] = None, ids: Optional[Sequence[torch.Tensor]] = None,
+               causal: bool = False, sep: bool = True) -> Plan:
+    lib = _lib.load()
+    B = masks[0].shape[0]
+    dev = masks[0].device
+    d = _lib.PlanDesc()
+    d.n_mods, d.batch, d.is_decoder, d.causal, d.sep = len(masks), B, int(decoder), int(causal), int(sep)
+    keep = []
+    total = 0
+    for i, m in enumerate(masks):
+        m = _req(m.reshape(B, -1), torch.bool, "mask").contiguous()
+        keep.append(m)
+        d.len[i], d.mod_id[i], d.mask[i] = m.shape[1], int(mod_ids[i]), m.data_ptr()
+        total += m.shape[1]
+        if decoder:
+            a = _req(attn_cnt[i].reshape(B, -1), torch.int32, "decoder_attention_mask").contiguous()
+            t = _req(ids[i].reshape(B, -1), torch.int64, "ids").contiguous()
+            keep += [a, t]
+            d.attn_cnt[i], d.ids[i] = a.data_ptr(), t.data_ptr()
+    budget = min(int(budget), total)
+    d.budget = budget
+    pl = Plan()
+    pl.B, pl.budget = B, budget
+    pl.keep_idx = torch.empty(B, budget, dtype=torch.int32, device=dev)
+    pl.keep_mod = torch.empty_like(pl.keep_idx)
+    pl.keep_pos = torch.empty_like(pl.keep_idx)
+    pl.pad = torch.empty(B, budget, dtype=torch.bool, device=dev)
+    pl.mod_mask = torch.empty(B, budget, dtype=torch.int16, device=dev)
+    pl.n_valid = torch.empty(B, dtype=torch.int32, device=dev)
+    pl.target_ids = pl.key_lo = pl.key_hi = None
+    if decoder:
+        pl.target_ids = torch.empty(B, budget, dtype=torch.int64, device=dev)
+        pl.key_lo = torch.empty(B, budget, dtype=torch.int32, device=dev)
+        pl.key_hi = torch.empty_like(pl.key_lo)
+    _lib.check(lib.egom2p_index_plan(C.byref(d), _p(pl.keep_idx), _p(pl.keep_mod), _p(pl.keep_pos), _p(pl.pad),
+                                     _p(pl.mod_mask), _p(pl.n_valid), _p(pl.target_ids), _p(pl.key_lo), _p(pl.key_hi),
+                                     _s()), "index_plan")
+    return pl
+
+
+# ----------------------------------------------------------------------------------------------- embedding
+def _embed_desc(dim, lens, vocabs, ids, tables, pos, mod):
+    d = _lib.EmbedDesc()
+    d.n_mods, d.dim = len(lens), dim
+    for i in range(len(lens)):
+        d.len[i], d.vocab[i] = lens[i], vocabs[i]
+        d.ids[i] = _p(ids[i]) if ids is not None else None
+        d.token_emb[i] = _p(tables[i]) if tables is not None else None
+        d.pos_emb[i], d.mod_emb[i] = _p(pos[i]), _p(mod[i])
+    return d
+
+
+def embed_gather_fwd(plan: Plan, dim: int, lens, vocabs, ids, tables, pos, mod, mask_token=None, want_emb=True):
+    lib = _lib.load()
+    rows = plan.B * plan.budget
+    dev = plan.keep_mod.device
+    x0 = torch.empty(plan.B, plan.budget, dim, dtype=f32, device=dev)
+    emb = torch.empty_like(x0) if want_emb else None
+    d = _embed_desc(dim, lens, vocabs, ids, tables, pos, mod)
+    _lib.check(lib.egom2p_embed_gather_fwd(C.byref(d), _p(mask_token), _p(plan.keep_mod), _p(plan.keep_pos), _p(plan.pad),
+                                           rows, plan.budget, _p(x0), _p(emb), _s()), "embed_gather_fwd")
+    return x0, emb
+
+
+def embed_gather_bwd(plan: Plan, dim: int, lens, vocabs, ids, pos, mod, dx0, demb, d_tables, d_mod, d_mask_token):
+    lib = _lib.load()
+    rows = plan.B * plan.budget
+    d = _embed_desc(dim, lens, vocabs, ids, None, pos, mod)
+    n = len(lens)
+    arr_t = (C.c_void_p * _lib.MAX_MODS)(*[(_p(t) if t is not None else None) for t in (d_tables or [None] * n)])
+    arr_m = (C.c_void_p * _lib.MAX_MODS)(*[(_p(t) if t is not None else None) for t in (d_mod or [None] * n)])
+    _lib.check(lib.egom2p_embed_gather_bwd(C.byref(d), _p(dx0), _p(demb), _p(plan.keep_mod), _p(plan.keep_pos),
+                                           _p(plan.pad), rows, plan.budget, C.cast(arr_t, C.c_void_p),
+                                           C.cast(arr_m, C.c_void_p), _p(d_mask_token), _s()), "embed_gather_bwd")
+
+
+# ----------------------------------------------------------------------------------------------- layernorm
+def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6, out_bf16=True, out_f32=False, save_stats=True):
+    lib = _lib.load()
+    _req(x, f32, "x"); _req(w, f32, "weight")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    yb = torch.empty(x.shape, dtype=bf16, device=x.device) if out_bf16 else None
+    yf = torch.empty_like(x) if out_f32 else None
+    mean = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
+    _lib.check(lib.egom2p_layernorm_fwd(_p(x), _p(w), rows, D, eps, _p(yb), _p(yf), _p(mean), _p(rstd), _s()), "layernorm_fwd")
+    return yb, yf, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x, w, mean, rstd, dx_in=None, d_weight=None, want_bf16=False):
+    lib = _lib.load()
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dx = torch.empty_like(x)
+    dxb = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    dyb = dy if dy.dtype == bf16 else None
+    dyf = dy if dy.dtype == f32 else None
+    _lib.check(lib.egom2p_layernorm_bwd(_p(dyb), _p(dyf), _p(x), _p(w), _p(mean), _p(rstd), _p(dx_in), rows, D, _p(dx),
+                                        _p(dxb), _p(d_weight), _s()), "layernorm_bwd")
+    return dx, dxb
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn=False, b_mn=False, bias=None, addend=None,
+         out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
+    """C[M,N] = op(A) op(B)^T (+bias) (+addend). A/B are 2-D bf16 tensors with unit inner stride (views allowed)."""
+    lib = _lib.load()
+    _req(A, bf16, "A"); _req(B, bf16, "B")
+    assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1
+    out = out_bf16 if out_bf16 is not None else out_f32
+    assert out is not None and out.stride(-1) == 1
+    ldc = out.stride(0)
+    if out_bf16 is not None and out_f32 is not None:
+        assert out_bf16.stride(0) == out_f32.stride(0)
+    _lib.check(lib.egom2p_gemm_bf16(_p(A), _p(B), M, N, K, A.stride(0), B.stride(0), int(a_mn), int(b_mn), _p(bias),
+                                    _p(addend), addend.stride(0) if addend is not None else 0, _p(out_bf16), _p(out_f32),
+                                    ldc, _s()), "gemm_bf16")
+    return out
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, *, bias=None, addend=None, out_dtype=bf16):
+    """y = x @ w^T, x (R,K) bf16, w (N,K) bf16."""
+    R, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(R, N, dtype=out_dtype, device=x.device)
+    gemm(x, w, R, N, K, bias=bias, addend=addend, out_bf16=y if out_dtype == bf16 else None,
+         out_f32=y if out_dtype == f32 else None)
+    return y
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, addend=None, out_dtype=bf16):
+    """dx = dy @ w, dy (R,N) bf16, w (N,K) bf16 (consumed MN-major, no transpose copy)."""
+    R, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(R, K, dtype=out_dtype, device=dy.device)
+    gemm(dy, w, R, K, N, b_mn=True, addend=addend, out_bf16=dx if out_dtype == bf16 else None,
+         out_f32=dx if out_dtype == f32 else None)
+    return dx
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False):
+    """dw = dy^T @ x, dy (R,N) bf16, x (R,K) bf16 -> (N,K) fp32 (both operands consumed MN-major)."""
+    R, N = dy.shape
+    K = x.shape[1]
+    if out is None:
+        out = torch.empty(N, K, dtype=f32, device=dy.device)
+    gemm(dy, x, N, K, R, a_mn=True, b_mn=True, addend=out if accumulate else None, out_f32=out)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- head + CE
+def ce_forward(y: torch.Tensor, w: torch.Tensor, target: torch.Tensor):
+    """Returns (loss_sum (1,) fp32, lse (R,) fp32) for logits = y @ w^T without materialising them."""
+    lib = _lib.load()
+    R, K = y.shape
+    V = w.shape[0]
+    nt = (V + 255) // 256
+    dev = y.device
+    pm = torch.empty(nt, R, dtype=f32, device=dev)
+    ps = torch.empty(nt, R, dtype=f32, device=dev)
+    tl = torch.zeros(R, dtype=f32, device=dev)
+    lse = torch.empty(R, dtype=f32, device=dev)
+    loss = torch.zeros(1, dtype=f32, device=dev)
+    _lib.check(lib.egom2p_ce_partials(_p(y), _p(w), _p(target), R, V, K, y.stride(0), w.stride(0), _p(pm), _p(ps), _p(tl), _s()),
+               "ce_partials")
+    _lib.check(lib.egom2p_ce_finalize(_p(pm), _p(ps), _p(tl), R, nt, _p(lse), _p(loss), _s()), "ce_finalize")
+    return loss, lse
+
+
+def ce_dlogits(y, w, target, lse, gscale: torch.Tensor, v0: int, vc: int, out: torch.Tensor):
+    lib = _lib.load()
+    R, K = y.shape
+    _lib.check(lib.egom2p_ce_dlogits(_p(y), _p(w), _p(target), _p(lse), _p(gscale), R, v0, vc, K, y.stride(0), w.stride(0),
+                                     _p(out), out.stride(0), _s()), "ce_dlogits")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def lse_stride(Mq: int) -> int:
+    return (Mq + 63) // 64 * 64
+
+
+def attn_fwd(q, k, v, B, H, Mq, Nk, key_lo=None, key_hi=None, scale=None, want_lse=True):
+    """q (B*Mq, >=H*64) / k, v (B*Nk, ...) bf16 2-D views with unit inner stride. Returns (o (B*Mq, H*64) bf16, lse)."""
+    lib = _lib.load()
+    scale = (64 ** -0.5) if scale is None else scale
+    o = torch.empty(B * Mq, H * 64, dtype=bf16, device=q.device)
+    lse = torch.empty(B, H, lse_stride(Mq), dtype=f32, device=q.device) if want_lse else None
+    _lib.check(lib.egom2p_attn_fwd(_p(q), _p(k) if Nk > 0 else None, _p(v) if Nk > 0 else None, B, H, Mq, Nk, q.stride(0),
+                                   k.stride(0) if Nk > 0 else 0, v.stride(0) if Nk > 0 else 0, _p(key_lo), _p(key_hi),
+                                   scale, _p(o), o.stride(0), _p(lse), _s()), "attn_fwd")
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, do, lse, B, H, Mq, Nk, dq, dk, dv, key_lo=None, key_hi=None, scale=None):
+    lib = _lib.load()
+    scale = (64 ** -0.5) if scale is None else scale
+    nbytes = lib.egom2p_attn_bwd_scratch_bytes(B, H, Mq)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    _lib.check(lib.egom2p_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), B, H, Mq, Nk, q.stride(0), k.stride(0),
+                                   v.stride(0), o.stride(0), _p(key_lo), _p(key_hi), scale, _p(scratch), _p(dq), _p(dk),
+                                   _p(dv), dq.stride(0), dk.stride(0), dv.stride(0), _s()), "attn_bwd")
+
+
+# ----------------------------------------------------------------------------------------------- elementwise
+def swiglu_fwd(ab: torch.Tensor):
+    lib = _lib.load()
+    rows, h2 = ab.shape
+    g = torch.empty(rows, h2 // 2, dtype=bf16, device=ab.device)
+    _lib.check(lib.egom2p_swiglu_fwd(_p(ab), rows, h2 // 2, _p(g), _s()), "swiglu_fwd")
+    return g
+
+
+def swiglu_bwd(ab: torch.Tensor, dg: torch.Tensor):
+    lib = _lib.load()
+    rows, h2 = ab.shape
+    dab = torch.empty_like(ab)
+    _lib.check(lib.egom2p_swiglu_bwd(_p(ab), _p(dg), rows, h2 // 2, _p(dab), _s()), "swiglu_bwd")
+    return dab
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    _req(src, f32, "src")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=bf16, device=src.device)
+    _lib.check(lib.egom2p_cast_f32_to_bf16(_p(src), _p(out), src.numel(), _s()), "cast_f32_to_bf16")
+    return out
+
+
+def add_f32(a, b, want_f32=True, want_bf16=False):
+    lib = _lib.load()
+    out = torch.empty_like(a) if want_f32 else None
+    outb = torch.empty(a.shape, dtype=bf16, device=a.device) if want_bf16 else None
+    _lib.check(lib.egom2p_add_f32(_p(a), _p(b), a.numel(), _p(out), _p(outb), _s()), "add_f32")
+    return out, outb
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=None):
+    lib = _lib.load()
+    _lib.check(lib.egom2p_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, wd, step, _p(grad_scale),
+                                     _s()), "adamw_step")
+
+
+def sumsq(x, out):
+    lib = _lib.load()
+    _lib.check(lib.egom2p_sumsq_f32(_p(x), x.numel(), _p(out), _s()), "sumsq_f32")
