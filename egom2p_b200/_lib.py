@@ -52,6 +52,9 @@ SIGNATURES = {
     "egom2p_add_f32": [vp, vp, i64, vp, vp, vp],
     "egom2p_adamw_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp],
     "egom2p_sumsq_f32": [vp, i64, vp, vp],
+    "egom2p_colsum_f32": [vp, i64, i32, vp, vp],
+    "egom2p_gather_rows_bf16": [vp, vp, i64, i32, vp, vp],
+    "egom2p_scatter_rows_f32": [vp, vp, i64, i32, vp, vp],
 }
 _RESTYPES = {"egom2p_last_error": C.c_char_p, "egom2p_launch_count": i64, "egom2p_attn_bwd_scratch_bytes": i64}
 

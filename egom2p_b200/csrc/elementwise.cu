@@ -137,7 +137,56 @@ __global__ void __launch_bounds__(kEwThreads) sumsq_kernel(const float* __restri
   }
 }
 
+// out[c] += sum_r x[r, c]; each CTA reduces a 64-row slab, threads own columns (coalesced), one atomic per column.
+__global__ void __launch_bounds__(kEwThreads) colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ out) {
+  const int64_t r0 = (int64_t)blockIdx.x * 64, r1 = min(r0 + 64, rows);
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += x[r * cols + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+// Row gather / scatter-add used to (un)compact the rows of one modality for its vocabulary head.
+__global__ void __launch_bounds__(kEwThreads) gather_rows_bf16_kernel(const uint16_t* __restrict__ src, const int64_t* __restrict__ idx,
+                                                                      int64_t n, int cols8, uint16_t* __restrict__ dst) {
+  const int64_t total = n * cols8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols8;
+    const int c = (int)(i - r * cols8);
+    reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[idx[r] * cols8 + c];
+  }
+}
+__global__ void __launch_bounds__(kEwThreads) scatter_rows_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                                                      int64_t n, int cols4, float* __restrict__ dst) {
+  const int64_t total = n * cols4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols4;
+    const int c = (int)(i - r * cols4);
+    reinterpret_cast<float4*>(dst)[idx[r] * cols4 + c] = reinterpret_cast<const float4*>(src)[i];
+  }
+}
+
 }  // namespace egom2p
+
+extern "C" int egom2p_colsum_f32(const float* x, int64_t rows, int32_t cols, float* out, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(x && out && rows > 0 && cols > 0, "colsum_f32: bad argument");
+  colsum_kernel<<<(unsigned)((rows + 63) / 64), kEwThreads, 0, (cudaStream_t)stream>>>(x, rows, cols, out);
+  return check_launch("colsum_f32");
+}
+extern "C" int egom2p_gather_rows_bf16(const uint16_t* src, const int64_t* idx, int64_t n, int32_t cols, uint16_t* dst, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(src && idx && dst && n > 0 && cols > 0 && cols % 8 == 0, "gather_rows_bf16: bad argument (cols %% 8 == 0)");
+  gather_rows_bf16_kernel<<<ew_grid(n * (cols / 8)), kEwThreads, 0, (cudaStream_t)stream>>>(src, idx, n, cols / 8, dst);
+  return check_launch("gather_rows_bf16");
+}
+extern "C" int egom2p_scatter_rows_f32(const float* src, const int64_t* idx, int64_t n, int32_t cols, float* dst, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(src && idx && dst && n > 0 && cols > 0 && cols % 4 == 0, "scatter_rows_f32: bad argument (cols %% 4 == 0)");
+  scatter_rows_f32_kernel<<<ew_grid(n * (cols / 4)), kEwThreads, 0, (cudaStream_t)stream>>>(src, idx, n, cols / 4, dst);
+  return check_launch("scatter_rows_f32");
+}
 
 extern "C" int egom2p_swiglu_fwd(const uint16_t* ab, int64_t rows, int32_t hidden, uint16_t* g, void* stream) {
   using namespace egom2p;

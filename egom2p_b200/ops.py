@@ -286,3 +286,27 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=None):
 def sumsq(x, out):
     lib = _lib.load()
     _lib.check(lib.egom2p_sumsq_f32(_p(x), x.numel(), _p(out), _s()), "sumsq_f32")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor):
+    lib = _lib.load()
+    rows, cols = x.shape
+    _lib.check(lib.egom2p_colsum_f32(_p(x), rows, cols, _p(out), _s()), "colsum_f32")
+    return out
+
+
+def gather_rows_bf16(src: torch.Tensor, idx: torch.Tensor):
+    lib = _lib.load()
+    n, cols = idx.numel(), src.shape[1]
+    dst = torch.empty(n, cols, dtype=bf16, device=src.device)
+    if n:
+        _lib.check(lib.egom2p_gather_rows_bf16(_p(src), _p(idx), n, cols, _p(dst), _s()), "gather_rows_bf16")
+    return dst
+
+
+def scatter_rows_f32(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor):
+    lib = _lib.load()
+    n, cols = idx.numel(), src.shape[1]
+    if n:
+        _lib.check(lib.egom2p_scatter_rows_f32(_p(src), _p(idx), n, cols, _p(dst), _s()), "scatter_rows_f32")
+    return dst

@@ -155,6 +155,12 @@ int egom2p_add_f32(const float* a, const float* b, int64_t n, float* out, uint16
 int egom2p_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* grad_scale,
                       void* stream);
+/* out[c] += sum_r x[r, c] -- bias gradient of decoder_proj_context (egom2p_model.py:157,722). */
+int egom2p_colsum_f32(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
+/* dst[i, :] = src[idx[i], :] (bf16) and dst[idx[i], :] = src[i, :] (fp32): compaction of the rows of one modality for
+ * its vocabulary head, replacing the boolean row-select y[decoder_mod_mask == id] (egom2p_model.py:633). */
+int egom2p_gather_rows_bf16(const uint16_t* src, const int64_t* idx, int64_t n, int32_t cols, uint16_t* dst, void* stream);
+int egom2p_scatter_rows_f32(const float* src, const int64_t* idx, int64_t n, int32_t cols, float* dst, void* stream);
 /* sumsq[0] += sum(x^2) (fp32 atomics) -- building block of clip_grad_norm_ (egom2p/utils/native_scaler.py:29-33). */
 int egom2p_sumsq_f32(const float* x, int64_t n, float* sumsq, void* stream);
 
