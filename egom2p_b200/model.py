@@ -172,7 +172,7 @@ class _EncoderBlockFn(torch.autograd.Function):
         wqkv, wproj, w13, w2 = wb
         x1, sa = _self_attn_fwd(x, n1w, wqkv, wproj, geom.B, geom.N, geom.H, geom.enc_lo, geom.enc_hi, geom.eps)
         x2, sm = _mlp_fwd(x1, n2w, w13, w2, geom.eps)
-        ctx.geom, ctx.wb = geom, wb
+        ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
         ctx.save_for_backward(x, n1w, n2w, x1, *sa, *sm)
         return x2
 
@@ -185,8 +185,8 @@ class _EncoderBlockFn(torch.autograd.Function):
         dx2 = dx2.contiguous()
         dx1, dx1b, dn2w, dw13, dw2 = _mlp_bwd(dx2, x1, n2w, w13, w2, sm)
         dx, dn1w, dwqkv, dwproj = _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, sa, g.B, g.N, g.H, g.enc_lo, g.enc_hi)
-        F = dw13.shape[0] // 2
-        return dx, dn1w, dwqkv, dwproj, dn2w, dw13[:F], dw2, dw13[F:], None, None
+        F, Fp = ctx.F, dw13.shape[0] // 2
+        return dx, dn1w, dwqkv, dwproj, dn2w, dw13[:F], dw2[:, :F], dw13[Fp:Fp + F], None, None
 
 
 class _DecoderBlockFn(torch.autograd.Function):
@@ -205,7 +205,7 @@ class _DecoderBlockFn(torch.autograd.Function):
         o2, lse2 = ops.attn_fwd(q, kv[:, :D], kv[:, D:], g.B, g.H, g.M, g.N, g.x_lo, g.x_hi)
         y2 = ops.linear_fwd(o2, wxproj, addend=y1, out_dtype=f32)
         y3, sm = _mlp_fwd(y2, n2w, w13, w2, g.eps)
-        ctx.geom, ctx.wb = geom, wb
+        ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
         ctx.save_for_backward(y, context, n1w, qnw, cnw, n2w, y1, y2, meanq, rstdq, hq, q, meanc, rstdc, hc, kv, o2, lse2,
                               *sa, *sm)
         return y3
@@ -234,8 +234,9 @@ class _DecoderBlockFn(torch.autograd.Function):
         dy1, dy1b = ops.layernorm_bwd(dhq, y1, qnw, meanq, rstdq, dx_in=dy2, d_weight=dqnw, want_bf16=True)
         dctx, _ = ops.layernorm_bwd(dhc, context, cnw, meanc, rstdc, d_weight=dcnw)
         dy, dn1w, dwqkv, dwsproj = _self_attn_bwd(dy1, dy1b, y, n1w, wqkv, wsproj, sa, g.B, g.M, g.H, g.dec_lo, g.dec_hi)
-        F = dw13.shape[0] // 2
-        return (dy, dctx, dn1w, dwqkv, dwsproj, dqnw, dcnw, dwq, dwkv, dwxproj, dn2w, dw13[:F], dw2, dw13[F:], None, None)
+        F, Fp = ctx.F, dw13.shape[0] // 2
+        return (dy, dctx, dn1w, dwqkv, dwsproj, dqnw, dcnw, dwq, dwkv, dwxproj, dn2w, dw13[:F], dw2[:, :F], dw13[Fp:Fp + F],
+                None, None)
 
 
 class _ContextFn(torch.autograd.Function):
@@ -479,16 +480,21 @@ class EgoM2P(nn.Module):
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
+        dev = params[0].device
         if len(params) == 1:
-            out = hit[1] if hit is not None and hit[1].shape == params[0].shape else None
-            wb = ops.cast_bf16(params[0].detach(), out)
-        else:  # row-wise concatenation (fc1 | fc3 -> one N = 2*hidden GEMM)
-            rows = sum(p.shape[0] for p in params)
-            wb = hit[1] if hit is not None else torch.empty(rows, params[0].shape[1], dtype=bf16, device=params[0].device)
-            r = 0
-            for p in params:
-                ops.cast_bf16(p.detach(), wb[r:r + p.shape[0]])
-                r += p.shape[0]
+            p = params[0]
+            pad = (-p.shape[1]) % 8
+            if pad == 0:
+                out = hit[1] if hit is not None and hit[1].shape == p.shape else None
+                wb = ops.cast_bf16(p.detach(), out)
+            else:  # inner dim padded with zero columns so TMA row pitches stay 16-byte multiples (e.g. hidden 682)
+                wb = hit[1] if hit is not None else torch.zeros(p.shape[0], p.shape[1] + pad, dtype=bf16, device=dev)
+                wb[:, :p.shape[1]].copy_(ops.cast_bf16(p.detach()))
+        else:  # row-wise concatenation (fc1 | fc3 -> one N = 2*hidden GEMM), each part padded to a multiple of 8 rows
+            rp = (params[0].shape[0] + 7) // 8 * 8
+            wb = hit[1] if hit is not None else torch.zeros(rp * len(params), params[0].shape[1], dtype=bf16, device=dev)
+            for i, p in enumerate(params):
+                ops.cast_bf16(p.detach(), wb[i * rp:i * rp + p.shape[0]])
         self._wcache[key] = (ver, wb)
         return wb
 
