@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- ego-b mod4 masked multimodal TRAINING step (BASELINE.json configs[1]) on N GPUs of one node.
+
+A "step" = one pass of the hot path over one synthetic batch: H2D-free forward (index plan, fused embed/gather, 12
+encoder + 12 decoder blocks, fused head + cross-entropy) + backward (+ DDP bucketed NCCL all-reduce for N > 1) +
+clip_grad_norm_(1.0) + AdamW, exactly the body of the reference's train_one_epoch (run_training_egom2p.py:701-746).
+Inputs: the "dense" synthetic regime of SURVEY.md section 8(d) (2048 encoder + 2048 decoder tokens per sample, all valid;
+1009 rgb + 1009 depth + 15 cam + 15 gaze on both sides), random-init ego-b weights (396.2 M params), bf16 tensor-core
+compute with fp32 masters / residual stream.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--impl reference]
+
+`value` = nominal tokens/s of the whole job (global batch x 4096 / step time, the reference's own accounting,
+run_training_egom2p.py:645-647) timed on the device with inputs resident in HBM; `e2e` = the same metric through the
+public model API with pinned-host inputs copied every step and the loss read back. `--impl reference` times the CPU
+restatement of the reference path (oracle/, fp32, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NOMINAL_TOKENS = 4096  # num_input_tokens + num_target_tokens per sample
+N_ENC = N_DEC = 2048
+SPLIT = {"tok_rgb": 1009, "tok_depth": 1009, "tok_cam": 15, "tok_gaze": 15}
+# algorithmic (mask-aware) FLOPs of one sample-step in the dense regime, SURVEY.md section 8(d): 3 x 1396.9 GFLOP
+FLOP_PER_SAMPLE_STEP = 4190.6e9
+
+
+def make_batch(b: int, seed: int, pin: bool):
+    """Synthetic mod_dict in the reference layout (egom2p/data/masking.py:236-266), CPU tensors."""
+    from egom2p_b200.modality_info import MODALITY_INFO as MI
+    rng = np.random.default_rng(seed)
+    md = {}
+    for m in sorted(MI):
+        L, V = MI[m]["max_tokens"], MI[m]["vocab_size"]
+        n = SPLIT[m]
+        ids = rng.integers(0, V, size=(b, L), dtype=np.int64)
+        imask = np.ones((b, L), dtype=bool)
+        tmask = np.ones((b, L), dtype=bool)
+        cnt = np.zeros((b, L), dtype=np.int32)
+        for i in range(b):
+            perm = rng.permutation(L)
+            imask[i, perm[:n]] = False
+            tmask[i, perm[n:2 * n]] = False
+            cnt[i, int(np.argmin(tmask[i]))] = n
+        t = torch.from_numpy(ids)
+        if L == 5120:
+            t = t.reshape(b, 5, 32, 32)
+        d = {"tensor": t, "input_mask": torch.from_numpy(imask), "target_mask": torch.from_numpy(tmask),
+             "decoder_attention_mask": torch.from_numpy(cnt)}
+        md[m] = {k: (v.pin_memory() if pin else v) for k, v in d.items()}
+    return md
+
+
+def md_bytes(md):
+    return int(sum(v.numel() * v.element_size() for d in md.values() for v in d.values()))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=10)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def build_model(device):
+    import egom2p_b200 as e
+    from egom2p_b200.modality_info import MODALITY_INFO as MI
+    torch.manual_seed(0)
+    mods = e.MOD4
+    model = e.create_model("egom2p_base_12e_12d_swiglu_nobias",
+                           encoder_embeddings={k: MI[k]["encoder_embedding"]() for k in mods},
+                           decoder_embeddings={k: MI[k]["decoder_embedding"]() for k in mods},
+                           modality_info={k: MI[k] for k in mods}, num_register_tokens=0)
+    return model.to(device)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def cpu_reference_step(b: int, threads: int):
+    """One fwd+bwd of the CPU fp32 restatement (oracle/) on ego-b, dense regime, batch b. Returns seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import egom2p_oracle as orc
+    import synth
+    torch.set_num_threads(threads)
+    cfg = synth.make_cfg(768, 12, 12, 12, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"])
+    sd = synth.make_state_dict(cfg, 0)
+    leaf = {}
+    for k, v in sd.items():
+        if k.endswith("to_logits.weight") or (k.startswith("decoder_embeddings") and k.endswith("mod_emb")):
+            continue
+        leaf[k] = v.requires_grad_(v.is_floating_point() and not k.endswith("pos_emb") and not (k.endswith(".bias") and "proj_context" not in k))
+    for m in cfg["mods"]:
+        leaf[f"decoder_embeddings.{m}.to_logits.weight"] = leaf[f"decoder_embeddings.{m}.token_emb.weight"]
+        leaf[f"decoder_embeddings.{m}.mod_emb"] = leaf[f"encoder_embeddings.{m}.mod_emb"]
+    md = make_batch(b, 1234, pin=False)
+    t0 = time.perf_counter()
+    out = orc.forward(leaf, cfg, md, N_ENC, N_DEC)
+    out["loss"].backward()
+    return time.perf_counter() - t0, float(out["loss"])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, loss = cpu_reference_step(1, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = NOMINAL_TOKENS / t
+    line = {"impl": "reference", "metric": "ego-b mod4 train nominal tokens/sec (whole job)", "value": val, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ego-b mod4 (396.2M) train step fwd+bwd, dense regime 2048 enc + 2048 dec tokens, CPU fp32",
+                       "global_batch": 1},
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port",
+                             "sample": "1 sample (4096 nominal tokens) fwd+bwd per step, oracle/egom2p_oracle.py (CPU fp32 restatement of the reference)"},
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("EGOM2P_BENCH_BATCH", "16")), help="samples per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = min(args.steps, 2)
+        args.warmup = min(args.warmup, 1)
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from egom2p_b200 import _lib, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b = args.batch
+    model = build_model(dev)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
+                                                        broadcast_buffers=False, gradient_as_bucket_view=True)
+    decay = [p for n, p in model.named_parameters() if not ("norm" in n or n.endswith(".bias"))]
+    no_decay = [p for n, p in model.named_parameters() if ("norm" in n or n.endswith(".bias"))]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}],
+                            lr=1e-4, betas=(0.9, 0.95), eps=1e-8, fused=True)
+    params = list(model.parameters())
+
+    host_batches = [make_batch(b, 1234 + rank * 1000 + s, pin=True) for s in range(2)]
+    dev_batches = [{m: {k: v.to(dev) for k, v in d.items()} for m, d in hb.items()} for hb in host_batches]
+
+    def step(md):
+        loss, mod_loss = net(md, N_ENC, N_DEC, loss_type="mod")
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then device-resident timing
+    for i in range(args.warmup):
+        step(dev_batches[i % 2])
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(lambda i: step(dev_batches[i % 2]), args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end through the public API: pinned host inputs copied every step, loss read back every step
+    def e2e_step(i):
+        md = {m: {k: v.to(dev, non_blocking=True) for k, v in d.items()} for m, d in host_batches[i % 2].items()}
+        loss = step(md)
+        return loss.item()
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    last_loss = e2e_step(0)
+
+    # ---- per-kernel-family breakdown of one extra step (CUDA events around each C-ABI launch)
+    with ops.KernelTimer() as kt:
+        step(dev_batches[0])
+    fam = kt.summary()
+
+    if rank == 0:
+        t_step = ms / args.steps / 1e3
+        gbatch = b * world
+        value = gbatch * NOMINAL_TOKENS / t_step
+        e2e_val = gbatch * NOMINAL_TOKENS / (ms_e2e / args.steps / 1e3)
+        hbm, tf_burst, tf_sus, src = peaks()
+        tflops = gbatch * FLOP_PER_SAMPLE_STEP / t_step / 1e12 / world  # per GPU
+        g = fam.get("gemm", {"ms": 1e-9, "work": 0.0, "launches": 1})
+        achieved = g["work"] / (g["ms"] / 1e3) / 1e12
+        total_kernel_ms = sum(d["ms"] for d in fam.values())
+        line = {
+            "metric": "ego-b mod4 train nominal tokens/sec (whole job)", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ego-b mod4 (egom2p_base_12e_12d_swiglu_nobias, 396.2M params) training step: fwd + bwd + "
+                                   "clip_grad_norm(1.0) + AdamW; dense synthetic regime, 2048 encoder + 2048 decoder tokens/sample "
+                                   "(1009 rgb + 1009 depth + 15 cam + 15 gaze per side), random-init weights",
+                       "global_batch": gbatch, "batch_per_gpu": b, "parallelism": f"dp{world}", "nominal_tokens_per_sample": NOMINAL_TOKENS,
+                       "l2_policy": "working set (activations + 1.6 GB weights) far exceeds the 126 MB L2; no explicit flush",
+                       "model_tflops_per_gpu": tflops, "mfu_vs_2250_spec": tflops / 2250.0,
+                       "mfu_vs_measured_sustained": tflops / tf_sus, "peaks_source": src, "loss": last_loss},
+            "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": md_bytes(host_batches[0]), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all nn.Linear fwd/dgrad/wgrad)",
+                         "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
+                         "traffic": None, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "share_of_kernel_time": g["ms"] / max(total_kernel_ms, 1e-9),
+                         "families": {k: {"ms": round(d["ms"], 3), "launches": d["launches"],
+                                          ("tflops" if d["unit"] == "flop" else "gbs"):
+                                              round(d["work"] / (d["ms"] / 1e3 + 1e-12) / (1e12 if d["unit"] == "flop" else 1e9), 1)}
+                                      for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            dts = [cpu_reference_step(1, cores)[0] for _ in range(args.cpu_steps)]
+            dt = float(np.mean(dts))
+            line["cpu_baseline"] = {"value": NOMINAL_TOKENS / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_steps} x (1 sample = 4096 nominal tokens, fwd+bwd, fp32) of the same dense workload via oracle/egom2p_oracle.py"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

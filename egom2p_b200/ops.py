@@ -17,6 +17,51 @@ def _s() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional per-family CUDA-event timing (bench.py's roofline line). When active, wrappers bracket their launches
+    with events on the current stream and record algorithmic work; `summary()` synchronises once at the end."""
+    active: Optional["KernelTimer"] = None
+
+    def __init__(self):
+        self.records = []  # (family, work, unit, start_event, end_event)
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out: Dict[str, Dict[str, float]] = {}
+        for fam, work, unit, e0, e1 in self.records:
+            d = out.setdefault(fam, {"ms": 0.0, "work": 0.0, "launches": 0, "unit": unit})
+            d["ms"] += e0.elapsed_time(e1)
+            d["work"] += work
+            d["launches"] += 1
+        return out
+
+
+class _timed:
+    __slots__ = ("fam", "work", "unit", "e0")
+
+    def __init__(self, fam: str, work: float, unit: str):
+        self.fam, self.work, self.unit = fam, work, unit
+
+    def __enter__(self):
+        if KernelTimer.active is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        t = KernelTimer.active
+        if t is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            t.records.append((self.fam, self.work, self.unit, self.e0, e1))
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -96,8 +141,9 @@ def embed_gather_fwd(plan: Plan, dim: int, lens, vocabs, ids, tables, pos, mod, 
     x0 = torch.empty(plan.B, plan.budget, dim, dtype=f32, device=dev)
     emb = torch.empty_like(x0) if want_emb else None
     d = _embed_desc(dim, lens, vocabs, ids, tables, pos, mod)
-    _lib.check(lib.egom2p_embed_gather_fwd(C.byref(d), _p(mask_token), _p(plan.keep_mod), _p(plan.keep_pos), _p(plan.pad),
-                                           rows, plan.budget, _p(x0), _p(emb), _s()), "embed_gather_fwd")
+    with _timed("embed_gather", rows * dim * 4.0 * (2 + (1 if mask_token is None else 0) + (1 if want_emb else 0)), "byte"):
+        _lib.check(lib.egom2p_embed_gather_fwd(C.byref(d), _p(mask_token), _p(plan.keep_mod), _p(plan.keep_pos), _p(plan.pad),
+                                               rows, plan.budget, _p(x0), _p(emb), _s()), "embed_gather_fwd")
     return x0, emb
 
 
@@ -123,7 +169,8 @@ def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6, out_bf16=
     yf = torch.empty_like(x) if out_f32 else None
     mean = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
-    _lib.check(lib.egom2p_layernorm_fwd(_p(x), _p(w), rows, D, eps, _p(yb), _p(yf), _p(mean), _p(rstd), _s()), "layernorm_fwd")
+    with _timed("layernorm_fwd", rows * D * (4.0 + (2 if out_bf16 else 0) + (4 if out_f32 else 0)), "byte"):
+        _lib.check(lib.egom2p_layernorm_fwd(_p(x), _p(w), rows, D, eps, _p(yb), _p(yf), _p(mean), _p(rstd), _s()), "layernorm_fwd")
     return yb, yf, mean, rstd
 
 
@@ -135,8 +182,10 @@ def layernorm_bwd(dy: torch.Tensor, x, w, mean, rstd, dx_in=None, d_weight=None,
     dxb = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
     dyb = dy if dy.dtype == bf16 else None
     dyf = dy if dy.dtype == f32 else None
-    _lib.check(lib.egom2p_layernorm_bwd(_p(dyb), _p(dyf), _p(x), _p(w), _p(mean), _p(rstd), _p(dx_in), rows, D, _p(dx),
-                                        _p(dxb), _p(d_weight), _s()), "layernorm_bwd")
+    nbytes = rows * D * (4.0 + dy.element_size() + 4 + (4 if dx_in is not None else 0) + (2 if want_bf16 else 0))
+    with _timed("layernorm_bwd", nbytes, "byte"):
+        _lib.check(lib.egom2p_layernorm_bwd(_p(dyb), _p(dyf), _p(x), _p(w), _p(mean), _p(rstd), _p(dx_in), rows, D, _p(dx),
+                                            _p(dxb), _p(d_weight), _s()), "layernorm_bwd")
     return dx, dxb
 
 
@@ -152,9 +201,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn=False
     ldc = out.stride(0)
     if out_bf16 is not None and out_f32 is not None:
         assert out_bf16.stride(0) == out_f32.stride(0)
-    _lib.check(lib.egom2p_gemm_bf16(_p(A), _p(B), M, N, K, A.stride(0), B.stride(0), int(a_mn), int(b_mn), _p(bias),
-                                    _p(addend), addend.stride(0) if addend is not None else 0, _p(out_bf16), _p(out_f32),
-                                    ldc, _s()), "gemm_bf16")
+    with _timed("gemm", 2.0 * M * N * K, "flop"):
+        _lib.check(lib.egom2p_gemm_bf16(_p(A), _p(B), M, N, K, A.stride(0), B.stride(0), int(a_mn), int(b_mn), _p(bias),
+                                        _p(addend), addend.stride(0) if addend is not None else 0, _p(out_bf16), _p(out_f32),
+                                        ldc, _s()), "gemm_bf16")
     return out
 
 
@@ -201,8 +251,9 @@ def ce_forward(y: torch.Tensor, w: torch.Tensor, target: torch.Tensor):
     tl = torch.zeros(R, dtype=f32, device=dev)
     lse = torch.empty(R, dtype=f32, device=dev)
     loss = torch.zeros(1, dtype=f32, device=dev)
-    _lib.check(lib.egom2p_ce_partials(_p(y), _p(w), _p(target), R, V, K, y.stride(0), w.stride(0), _p(pm), _p(ps), _p(tl), _s()),
-               "ce_partials")
+    with _timed("head_ce", 2.0 * R * V * K, "flop"):
+        _lib.check(lib.egom2p_ce_partials(_p(y), _p(w), _p(target), R, V, K, y.stride(0), w.stride(0), _p(pm), _p(ps), _p(tl),
+                                          _s()), "ce_partials")
     _lib.check(lib.egom2p_ce_finalize(_p(pm), _p(ps), _p(tl), R, nt, _p(lse), _p(loss), _s()), "ce_finalize")
     return loss, lse
 
@@ -210,8 +261,9 @@ def ce_forward(y: torch.Tensor, w: torch.Tensor, target: torch.Tensor):
 def ce_dlogits(y, w, target, lse, gscale: torch.Tensor, v0: int, vc: int, out: torch.Tensor):
     lib = _lib.load()
     R, K = y.shape
-    _lib.check(lib.egom2p_ce_dlogits(_p(y), _p(w), _p(target), _p(lse), _p(gscale), R, v0, vc, K, y.stride(0), w.stride(0),
-                                     _p(out), out.stride(0), _s()), "ce_dlogits")
+    with _timed("head_ce", 2.0 * R * vc * K, "flop"):
+        _lib.check(lib.egom2p_ce_dlogits(_p(y), _p(w), _p(target), _p(lse), _p(gscale), R, v0, vc, K, y.stride(0), w.stride(0),
+                                         _p(out), out.stride(0), _s()), "ce_dlogits")
     return out
 
 
@@ -226,9 +278,10 @@ def attn_fwd(q, k, v, B, H, Mq, Nk, key_lo=None, key_hi=None, scale=None, want_l
     scale = (64 ** -0.5) if scale is None else scale
     o = torch.empty(B * Mq, H * 64, dtype=bf16, device=q.device)
     lse = torch.empty(B, H, lse_stride(Mq), dtype=f32, device=q.device) if want_lse else None
-    _lib.check(lib.egom2p_attn_fwd(_p(q), _p(k) if Nk > 0 else None, _p(v) if Nk > 0 else None, B, H, Mq, Nk, q.stride(0),
-                                   k.stride(0) if Nk > 0 else 0, v.stride(0) if Nk > 0 else 0, _p(key_lo), _p(key_hi),
-                                   scale, _p(o), o.stride(0), _p(lse), _s()), "attn_fwd")
+    with _timed("attn_fwd", 4.0 * B * H * Mq * Nk * 64, "flop"):
+        _lib.check(lib.egom2p_attn_fwd(_p(q), _p(k) if Nk > 0 else None, _p(v) if Nk > 0 else None, B, H, Mq, Nk, q.stride(0),
+                                       k.stride(0) if Nk > 0 else 0, v.stride(0) if Nk > 0 else 0, _p(key_lo), _p(key_hi),
+                                       scale, _p(o), o.stride(0), _p(lse), _s()), "attn_fwd")
     return o, lse
 
 
@@ -237,9 +290,10 @@ def attn_bwd(q, k, v, o, do, lse, B, H, Mq, Nk, dq, dk, dv, key_lo=None, key_hi=
     scale = (64 ** -0.5) if scale is None else scale
     nbytes = lib.egom2p_attn_bwd_scratch_bytes(B, H, Mq)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
-    _lib.check(lib.egom2p_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), B, H, Mq, Nk, q.stride(0), k.stride(0),
-                                   v.stride(0), o.stride(0), _p(key_lo), _p(key_hi), scale, _p(scratch), _p(dq), _p(dk),
-                                   _p(dv), dq.stride(0), dk.stride(0), dv.stride(0), _s()), "attn_bwd")
+    with _timed("attn_bwd", 10.0 * B * H * Mq * Nk * 64, "flop"):
+        _lib.check(lib.egom2p_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), B, H, Mq, Nk, q.stride(0), k.stride(0),
+                                       v.stride(0), o.stride(0), _p(key_lo), _p(key_hi), scale, _p(scratch), _p(dq), _p(dk),
+                                       _p(dv), dq.stride(0), dk.stride(0), dv.stride(0), _s()), "attn_bwd")
 
 
 # ----------------------------------------------------------------------------------------------- elementwise
@@ -247,7 +301,8 @@ def swiglu_fwd(ab: torch.Tensor):
     lib = _lib.load()
     rows, h2 = ab.shape
     g = torch.empty(rows, h2 // 2, dtype=bf16, device=ab.device)
-    _lib.check(lib.egom2p_swiglu_fwd(_p(ab), rows, h2 // 2, _p(g), _s()), "swiglu_fwd")
+    with _timed("swiglu", rows * h2 * 3.0, "byte"):
+        _lib.check(lib.egom2p_swiglu_fwd(_p(ab), rows, h2 // 2, _p(g), _s()), "swiglu_fwd")
     return g
 
 
@@ -255,7 +310,8 @@ def swiglu_bwd(ab: torch.Tensor, dg: torch.Tensor):
     lib = _lib.load()
     rows, h2 = ab.shape
     dab = torch.empty_like(ab)
-    _lib.check(lib.egom2p_swiglu_bwd(_p(ab), _p(dg), rows, h2 // 2, _p(dab), _s()), "swiglu_bwd")
+    with _timed("swiglu", rows * h2 * 5.0, "byte"):
+        _lib.check(lib.egom2p_swiglu_bwd(_p(ab), _p(dg), rows, h2 // 2, _p(dab), _s()), "swiglu_bwd")
     return dab
 
 
@@ -265,7 +321,8 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None):
     src = src.contiguous()
     if out is None:
         out = torch.empty(src.shape, dtype=bf16, device=src.device)
-    _lib.check(lib.egom2p_cast_f32_to_bf16(_p(src), _p(out), src.numel(), _s()), "cast_f32_to_bf16")
+    with _timed("cast", src.numel() * 6.0, "byte"):
+        _lib.check(lib.egom2p_cast_f32_to_bf16(_p(src), _p(out), src.numel(), _s()), "cast_f32_to_bf16")
     return out
 
 
