@@ -23,6 +23,11 @@ constexpr int kQT = 128;     // query rows per CTA (fwd, dQ) / key rows per CTA 
 constexpr int kKB = 64;      // inner block (keys in fwd/dQ, query rows in dKV)
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2 (exp2f adds range fix-ups the softmax does not need)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {  // byte offset of 16-byte chunk in a [rows][128 B] SW128 tile
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
@@ -63,7 +68,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = kv_empty + kFwdStages;
   uint64_t* p_full = s_full + 1;
   uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* s_free = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 1);
   int* s_range = reinterpret_cast<int*>(tmem_slot + 1);  // [0] = lo, [1] = hi
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -75,6 +81,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
+    mbar_init(s_free, 128);
     fence_mbar_init();
     s_range[0] = INT_MAX;
     s_range[1] = INT_MIN;
@@ -129,15 +136,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(s_full);
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kFwdStages;
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * kKB * 128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tO, umma_desc_kmajor_sw128(aP + k * 32), umma_desc_mnmajor_sw128(aV + k * 2048, 8192), idesc_pv, k ? 1u : 0u);
-        umma_commit(o_full);
-        if (j + 1 < nblk) {
+        if (j + 1 < nblk) {  // S(j+1) as soon as S(j) sits in registers: overlaps the softmax of block j
           const int st1 = (j + 1) % kFwdStages;
+          mbar_wait(s_free, j & 1);
           mbar_wait(&kv_full[st1], ((j + 1) / kFwdStages) & 1);
           tc_fence_after();
           const uint32_t aK = smem_u32(sK + st1 * kKB * 128);
@@ -146,6 +147,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_bf16_ss(tS, umma_desc_kmajor_sw128(aQ + k * 32), umma_desc_kmajor_sw128(aK + k * 32), idesc_s, k ? 1u : 0u);
           umma_commit(s_full);
         }
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sV + st * kKB * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tO, umma_desc_kmajor_sw128(aP + k * 32), umma_desc_mnmajor_sw128(aV + k * 2048, 8192), idesc_pv, k ? 1u : 0u);
+        umma_commit(o_full);
         umma_commit(&kv_empty[st]);
       }
     }
@@ -164,31 +172,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(tmem_base + lane_addr, v0);
       tmem_ld32(tmem_base + lane_addr + 32, v1);
       tmem_ld_wait();
-      float x[kKB];
-      float bm = -INFINITY;
+      tc_fence_before();
+      mbar_arrive(s_free);
+      float sc = rscale;
+      if (!(rscale != 0.f && kv0 >= lo && kv0 + kKB <= hi)) {  // block touches the range boundary (or uniform row)
+        sc = rscale != 0.f ? rscale : 1.f;
 #pragma unroll
-      for (int c = 0; c < kKB; ++c) {
-        const float s = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
-        const int kidx = kv0 + c;
-        x[c] = (kidx >= lo && kidx < hi) ? s * rscale : -INFINITY;
-        bm = fmaxf(bm, x[c]);
+        for (int c = 0; c < 32; ++c) {
+          const bool ok0 = (kv0 + c >= lo) && (kv0 + c < hi), ok1 = (kv0 + 32 + c >= lo) && (kv0 + 32 + c < hi);
+          v0[c] = ok0 ? (rscale != 0.f ? v0[c] : 0u) : 0xff800000u;
+          v1[c] = ok1 ? (rscale != 0.f ? v1[c] : 0u) : 0xff800000u;
+        }
       }
+      float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        bm0 = fmaxf(bm0, fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c])));
+        bm1 = fmaxf(bm1, fmaxf(__uint_as_float(v0[c + 1]), __uint_as_float(v1[c + 1])));
+        bm2 = fmaxf(bm2, fmaxf(__uint_as_float(v0[c + 2]), __uint_as_float(v1[c + 2])));
+        bm3 = fmaxf(bm3, fmaxf(__uint_as_float(v0[c + 3]), __uint_as_float(v1[c + 3])));
+      }
+      const float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3)) * sc;  // sc > 0, so max commutes with the scaling
       const float m_new = fmaxf(m, bm);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m - m_use);
-      float sum = 0.f;
+      const float alpha = ex2(m - m_use);
+      const float nm = -m_use;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
       for (int c8 = 0; c8 < kKB / 8; ++c8) {
         float e[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          e[u] = exp2f(x[c8 * 8 + u] - m_use);
-          sum += e[u];
+          const int c = c8 * 8 + u;
+          e[u] = ex2(fmaf(__uint_as_float(c < 32 ? v0[c] : v1[c - 32]), sc, nm));
         }
+        sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
         uint4 pk;
         pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
         *reinterpret_cast<uint4*>(sP + swz_off(tid, c8)) = pk;
       }
+      const float sum = (sum0 + sum1) + (sum2 + sum3);
       l = l * alpha + sum;
       m = m_new;
       fence_async_smem();

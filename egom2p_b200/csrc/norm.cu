@@ -169,7 +169,7 @@ extern "C" int egom2p_layernorm_bwd(const uint16_t* dy_bf16, const float* dy_f32
   EGO_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_bwd: exactly one of dy_bf16 / dy_f32");
   EGO_REQUIRE(x && weight && mean && rstd && dx_out && rows > 0, "layernorm_bwd: null argument");
   EGO_REQUIRE(dim % 4 == 0 && dim > 0 && dim <= kLnMaxVec * 128, "layernorm_bwd: dim %d unsupported", dim);
-  const int rows_per_cta = 64;
+  const int rows_per_cta = 32;
   const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
   const size_t smem = (size_t)8 * dim * sizeof(float);
   const int nv = (dim / 4 + 31) / 32;
