@@ -1,10 +1,11 @@
 // bf16 GEMM on the 5th-gen tensor cores: tcgen05.mma (cta_group::1, 128 x BN x 16) with fp32 accumulators in TMEM,
-// operands staged by TMA (128B swizzle) through an mbarrier ring, persistent over output tiles with a double-buffered
-// accumulator so the epilogue of tile i overlaps the main loop of tile i+1.
+// operands staged by TMA (128B swizzle) through an mbarrier ring, persistent over (tile, k-split) work items with a
+// double-buffered accumulator so the epilogue of item i overlaps the main loop of item i+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
-// (TMEM -> registers -> per-warp smem transpose -> coalesced global stores with fused bias / residual add, or the
-// cross-entropy epilogues that never write logits to HBM).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
+// (two warps per TMEM lane quarter, each owning half of the tile's columns): TMEM -> registers -> (+bias, +residual,
+// or the cross-entropy transforms) -> swizzled smem box -> TMA store. Split-K work items (wgrad: few output tiles,
+// very long K) accumulate with TMA reduce-add, so there are no per-thread atomics and no bounds code.
 //
 // Operand majors (see include/egom2p_b200.h): K-major tiles are [rows][64 k] (one TMA box); MN-major tiles are
 // [64 k][64 mn] boxes, one per 64 rows of the tile, consumed through MN-major UMMA descriptors -- this is what lets
@@ -15,20 +16,19 @@ namespace egom2p {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
-constexpr int kStagePitch = 36;  // floats; 16-byte aligned rows, conflict-free float4 phases
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 enum { EPI_STORE = 0, EPI_CE_PARTIAL = 1, EPI_CE_DLOGITS = 2 };
 
 struct GemmParams {
   int M, N, K;
+  int splits;  // k-splits per output tile (1 = plain store, > 1 = TMA reduce-add into c_f32)
   // EPI_STORE
   const float* bias;
   const float* addend;
   int64_t ld_add;
-  uint16_t* c_bf16;
-  float* c_f32;
-  int64_t ldc;
+  int out_bf16, out_f32;
   // CE epilogues
   const int64_t* target;
   const float* lse;
@@ -45,21 +45,26 @@ struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 4 * 32 * kStagePitch * 4;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // one 32-row x 128-byte swizzled box per epilogue warp
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // + alignment slack
 };
 
+__device__ __forceinline__ uint32_t box_off(int row, int chunk) {  // 16-byte chunk inside a [32][128 B] SW128 box
+  return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmCb, const __grid_constant__ CUtensorMap tmCf, const GemmParams p) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::kABytes;
-  float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
+  uint8_t* staging = smem + kStages * S::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
@@ -68,8 +73,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  const int total_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
+  const int splits = p.splits;
+  const int kb_per = (k_blocks + splits - 1) / splits;
+  const int total_items = m_tiles * n_tiles * splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -80,7 +87,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -95,9 +102,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int tile = item / splits, split = item - tile * splits;
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int k0 = kb * BK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], S::kStageBytes);
@@ -126,13 +135,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int split = item % splits;
+        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
@@ -141,45 +152,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? umma_desc_mnmajor_sw128(a_addr + k * 2048, 8192) : umma_desc_kmajor_sw128(a_addr + k * 32);
             const uint64_t db = B_MN ? umma_desc_mnmajor_sw128(b_addr + k * 2048, 8192) : umma_desc_kmajor_sw128(b_addr + k * 32);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* st = staging + (warp - 2) * 32 * kStagePitch;
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the tile's columns
+    uint8_t* box = staging + (warp - 2) * 4096;
+    constexpr int kHalfCols = BN / 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int tile = item / splits;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_blk = tile % n_tiles;
-      const int m0 = (tile / n_tiles) * BM, n0 = n_blk * BN;
+      const int m0 = (tile / n_tiles) * BM, n0 = n_blk * BN + half * kHalfCols;
+      const int row0 = m0 + q * 32;
+      const int my_row = row0 + lane;
+      const bool row_ok = my_row < p.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int my_row = m0 + q * 32 + lane;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * kHalfCols;
       float row_lse = 0.f, gs = 0.f;
       int row_tgt = -1;
       float run_max = -INFINITY, run_sum = 0.f, tl = 0.f;
       bool has_tl = false;
-      if (EPI != EPI_STORE && my_row < p.M) {
+      if (EPI != EPI_STORE && row_ok) {
         row_tgt = (int)p.target[my_row] - p.v0;
         if (EPI == EPI_CE_DLOGITS) {
           row_lse = p.lse[my_row];
           gs = *p.gscale;
         }
       }
+      if (EPI == EPI_CE_PARTIAL) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        const int cbase = n0 + c * 32;
-        if (EPI == EPI_CE_PARTIAL) {
+        for (int c = 0; c < kHalfCols / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          const int cbase = n0 + c * 32;
           float cm = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -196,56 +213,107 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             run_sum = run_sum * __expf(run_max - nm) + s;
             run_max = nm;
           }
-          continue;
         }
-        if (EPI == EPI_CE_DLOGITS) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float pr = __expf(__uint_as_float(v[j]) - row_lse);
-            if (cbase + j == row_tgt) pr -= 1.f;
-            v[j] = __float_as_uint(pr * gs);
-          }
+        if (row_ok) {
+          const int64_t o = (int64_t)(n_blk * 2 + half) * p.M + my_row;
+          p.part_max[o] = run_max;
+          p.part_sum[o] = run_sum;
+          if (has_tl) p.tgt_logit[my_row] = tl;
         }
+      } else if (EPI == EPI_CE_DLOGITS || p.out_bf16) {
+        // ---- bf16 output: 64 columns (one 128-byte box row) per step
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols / 64; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(t_addr + c * 64, v0);
+          tmem_ld32(t_addr + c * 64 + 32, v1);
+          tmem_ld_wait();
+          const int cbase = n0 + c * 64;
+          if (EPI == EPI_CE_DLOGITS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(st + lane * kStagePitch + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int colv = 4 * (lane & 7);
-        const int gc = cbase + colv;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = (lane >> 3) + 4 * i;
-          const int gr = m0 + q * 32 + r;
-          if (gr < p.M && gc < p.N) {
-            float4 o = *reinterpret_cast<const float4*>(st + r * kStagePitch + colv);
-            if (p.bias) {
-              const float4 bv = *reinterpret_cast<const float4*>(p.bias + gc);
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            }
-            if (p.addend) {
-              const float4 av = *reinterpret_cast<const float4*>(p.addend + (int64_t)gr * p.ld_add + gc);
-              o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
-            }
-            if (p.c_f32) *reinterpret_cast<float4*>(p.c_f32 + (int64_t)gr * p.ldc + gc) = o;
-            if (p.c_bf16) {
-              uint2 pk;
-              pk.x = pack_bf16(o.x, o.y);
-              pk.y = pack_bf16(o.z, o.w);
-              *reinterpret_cast<uint2*>(p.c_bf16 + (int64_t)gr * p.ldc + gc) = pk;
+            for (int j = 0; j < 32; ++j) {
+              float p0 = __expf(__uint_as_float(v0[j]) - row_lse), p1 = __expf(__uint_as_float(v1[j]) - row_lse);
+              if (cbase + j == row_tgt) p0 -= 1.f;
+              if (cbase + 32 + j == row_tgt) p1 -= 1.f;
+              v0[j] = __float_as_uint(p0 * gs);
+              v1[j] = __float_as_uint(p1 * gs);
             }
           }
+          tma_store_wait_read();   // previous store out of this warp's box has been read
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
+            pk.y = pack_bf16(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
+            pk.z = pack_bf16(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
+            pk.w = pack_bf16(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
+            *reinterpret_cast<uint4*>(box + box_off(lane, j)) = pk;
+            pk.x = pack_bf16(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
+            pk.y = pack_bf16(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
+            pk.z = pack_bf16(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
+            pk.w = pack_bf16(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
+            *reinterpret_cast<uint4*>(box + box_off(lane, j + 4)) = pk;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && cbase < p.N) {
+            tma_store_2d(&tmCb, box, cbase, row0);
+            tma_store_commit();
+          }
         }
-        __syncwarp();
-      }
-      if (EPI == EPI_CE_PARTIAL && my_row < p.M) {
-        p.part_max[(int64_t)n_blk * p.M + my_row] = run_max;
-        p.part_sum[(int64_t)n_blk * p.M + my_row] = run_sum;
-        if (has_tl) p.tgt_logit[my_row] = tl;
+      } else {
+        // ---- fp32 output (+bias, +residual / accumulate): 32 columns (one 128-byte box row) per step
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          const int cbase = n0 + c * 32;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (cbase + 4 * j < p.N) {
+                const float4 bv = *reinterpret_cast<const float4*>(p.bias + cbase + 4 * j);
+                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + bv.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + bv.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + bv.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + bv.w);
+              }
+            }
+          }
+          if (p.addend && splits == 1 && row_ok) {
+            const float* arow = p.addend + (int64_t)my_row * p.ld_add + cbase;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (cbase + 4 * j < p.N) {
+                const float4 av = *reinterpret_cast<const float4*>(arow + 4 * j);
+                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + av.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + av.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + av.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + av.w);
+              }
+            }
+          }
+          tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(box + box_off(lane, j)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && cbase < p.N) {
+            if (splits > 1) tma_reduce_add_2d(&tmCf, box, cbase, row0);
+            else tma_store_2d(&tmCf, box, cbase, row0);
+            tma_store_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    tma_store_wait_all();  // global writes complete before the CTA exits
   }
 
   tc_fence_before();
@@ -256,10 +324,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+static int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_t ldb, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_t ldb, uint16_t* c_bf16, float* c_f32,
+                       int64_t ldc, GemmParams p, cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmCb, tmCf;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&tmA, A, p.M, p.K, lda, BM, BK);
   else       rc = make_tmap_bf16_2d(&tmA, A, p.K, p.M, lda, BK, 64);
@@ -267,6 +347,12 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   if (!B_MN) rc = make_tmap_bf16_2d(&tmB, B, p.N, p.K, ldb, BN, BK);
   else       rc = make_tmap_bf16_2d(&tmB, B, p.K, p.N, ldb, BK, 64);
   if (rc) return rc;
+  tmCb = tmA;
+  tmCf = tmA;
+  if (c_bf16 && (rc = make_tmap_2d(&tmCb, c_bf16, 2, p.M, p.N, ldc, 32, 64))) return rc;
+  if (c_f32 && (rc = make_tmap_2d(&tmCf, c_f32, 4, p.M, p.N, ldc, 32, 32))) return rc;
+  p.out_bf16 = c_bf16 != nullptr;
+  p.out_f32 = c_f32 != nullptr;
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -277,25 +363,37 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
     }
     attr_set = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  static int cached_sms = 0;
-  if (!cached_sms) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cached_sms > 0) sms = cached_sms;
+  const int sms = sm_count();
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  const int k_blocks = (p.K + BK - 1) / BK;
+  // split-K: only for fp32 accumulate/plain outputs, when the output tiles cannot fill the machine and K is long
+  int splits = 1;
+  if (EPI == EPI_STORE && !c_bf16 && !p.bias && (!p.addend || p.addend == c_f32) && tiles < sms && k_blocks >= 16) {
+    splits = (2 * sms + tiles - 1) / tiles;
+    splits = splits < k_blocks / 8 ? splits : k_blocks / 8;
+    if (splits < 1) splits = 1;
+    const int kb_per = (k_blocks + splits - 1) / splits;
+    splits = (k_blocks + kb_per - 1) / kb_per;  // no empty splits
+  }
+  p.splits = splits;
+  if (splits > 1 && !p.addend) {  // reduce-add needs a zeroed destination (an aliased addend means "accumulate into C")
+    cudaError_t e = cudaMemset2DAsync(c_f32, ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), p.M, stream);
+    if (e != cudaSuccess) { set_error("gemm: memset: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
+  }
+  const int items = tiles * splits;
+  const int grid = items < sms ? items : sms;
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmCb, tmCf, p);
   return check_launch("gemm_bf16");
 }
 
 template <int EPI>
 static int dispatch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_t ldb, int a_mn, int b_mn,
-                         const GemmParams& p, cudaStream_t stream) {
+                         uint16_t* c_bf16, float* c_f32, int64_t ldc, const GemmParams& p, cudaStream_t stream) {
   // BN = 256 halves B re-reads per tile; BN = 128 gives better wave quantisation on small problems.
   const int sms = 148;
   const int64_t tiles256 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + 255) / 256);
-  const bool use256 = (EPI != EPI_STORE) || (p.N >= 256 && tiles256 >= 2 * sms);
-#define EGO_GEMM_CASE(BN_, AM, BMJ) return launch_gemm<BN_, AM, BMJ, EPI>(A, B, lda, ldb, p, stream)
+  const bool use256 = (EPI != EPI_STORE) || (p.N >= 256 && (tiles256 >= 2 * sms || !c_bf16));
+#define EGO_GEMM_CASE(BN_, AM, BMJ) return launch_gemm<BN_, AM, BMJ, EPI>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream)
   if constexpr (EPI != EPI_STORE) {  // CE epilogues: Y (K-major) x W (K-major)
     EGO_GEMM_CASE(256, false, false);
   } else if (use256) {
@@ -319,11 +417,12 @@ extern "C" int egom2p_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M,
                                 int64_t ld_add, uint16_t* c_bf16, float* c_f32, int64_t ldc, void* stream) {
   using namespace egom2p;
   EGO_REQUIRE(A && B && M > 0 && N > 0 && K > 0, "gemm_bf16: null operand or empty shape (M=%d N=%d K=%d)", M, N, K);
-  EGO_REQUIRE(c_bf16 || c_f32, "gemm_bf16: no output");
+  EGO_REQUIRE((c_bf16 != nullptr) != (c_f32 != nullptr), "gemm_bf16: exactly one of c_bf16 / c_f32");
   EGO_REQUIRE(N % 4 == 0 && ldc % 4 == 0 && (!addend || ld_add % 4 == 0), "gemm_bf16: N, ldc, ld_add must be multiples of 4");
+  EGO_REQUIRE(!c_bf16 || (N % 8 == 0 && ldc % 8 == 0), "gemm_bf16: bf16 output needs N, ldc multiples of 8");
   GemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.bias = bias; p.addend = addend; p.ld_add = ld_add; p.c_bf16 = c_bf16; p.c_f32 = c_f32; p.ldc = ldc;
-  return dispatch_gemm<EPI_STORE>(A, B, lda, ldb, a_mn, b_mn, p, (cudaStream_t)stream);
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.addend = addend; p.ld_add = ld_add;
+  return dispatch_gemm<EPI_STORE>(A, B, lda, ldb, a_mn, b_mn, c_bf16, c_f32, ldc, p, (cudaStream_t)stream);
 }
 
 extern "C" int egom2p_ce_partials(const uint16_t* Y, const uint16_t* W, const int64_t* target, int32_t R, int32_t V, int32_t K,
@@ -332,7 +431,7 @@ extern "C" int egom2p_ce_partials(const uint16_t* Y, const uint16_t* W, const in
   EGO_REQUIRE(Y && W && target && part_max && part_sum && tgt_logit && R > 0 && V > 0 && K > 0, "ce_partials: bad argument");
   GemmParams p{};
   p.M = R; p.N = V; p.K = K; p.target = target; p.v0 = 0; p.part_max = part_max; p.part_sum = part_sum; p.tgt_logit = tgt_logit;
-  return dispatch_gemm<EPI_CE_PARTIAL>(Y, W, ldy, ldw, 0, 0, p, (cudaStream_t)stream);
+  return dispatch_gemm<EPI_CE_PARTIAL>(Y, W, ldy, ldw, 0, 0, nullptr, nullptr, 0, p, (cudaStream_t)stream);
 }
 
 extern "C" int egom2p_ce_dlogits(const uint16_t* Y, const uint16_t* W, const int64_t* target, const float* lse,
@@ -340,22 +439,25 @@ extern "C" int egom2p_ce_dlogits(const uint16_t* Y, const uint16_t* W, const int
                                  uint16_t* dlogits, int64_t ldd, void* stream) {
   using namespace egom2p;
   EGO_REQUIRE(Y && W && target && lse && gscale && dlogits && R > 0 && Vc > 0 && K > 0 && v0 >= 0, "ce_dlogits: bad argument");
-  EGO_REQUIRE(Vc % 4 == 0 && ldd % 4 == 0, "ce_dlogits: Vc and ldd must be multiples of 4");
+  EGO_REQUIRE(Vc % 8 == 0 && ldd % 8 == 0, "ce_dlogits: Vc and ldd must be multiples of 8");
   GemmParams p{};
-  p.M = R; p.N = Vc; p.K = K; p.target = target; p.lse = lse; p.gscale = gscale; p.v0 = v0; p.c_bf16 = dlogits; p.ldc = ldd;
-  return dispatch_gemm<EPI_CE_DLOGITS>(Y, W + (int64_t)v0 * ldw, ldy, ldw, 0, 0, p, (cudaStream_t)stream);
+  p.M = R; p.N = Vc; p.K = K; p.target = target; p.lse = lse; p.gscale = gscale; p.v0 = v0;
+  return dispatch_gemm<EPI_CE_DLOGITS>(Y, W + (int64_t)v0 * ldw, ldy, ldw, 0, 0, dlogits, nullptr, ldd, p, (cudaStream_t)stream);
 }
 
 namespace egom2p {
 __global__ void ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ tl,
-                                   int R, int n_tiles, float* __restrict__ lse, float* __restrict__ loss_sum) {
+                                   int R, int n_parts, float* __restrict__ lse, float* __restrict__ loss_sum) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   float contrib = 0.f;
   if (r < R) {
     float m = -INFINITY;
-    for (int t = 0; t < n_tiles; ++t) m = fmaxf(m, pm[(int64_t)t * R + r]);
+    for (int t = 0; t < n_parts; ++t) m = fmaxf(m, pm[(int64_t)t * R + r]);
     float s = 0.f;
-    for (int t = 0; t < n_tiles; ++t) s += ps[(int64_t)t * R + r] * __expf(pm[(int64_t)t * R + r] - m);
+    for (int t = 0; t < n_parts; ++t) {
+      const float pmv = pm[(int64_t)t * R + r];
+      if (pmv > -INFINITY) s += ps[(int64_t)t * R + r] * __expf(pmv - m);
+    }
     const float l = m + logf(s);
     lse[r] = l;
     contrib = l - tl[r];

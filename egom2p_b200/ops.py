@@ -244,7 +244,7 @@ def ce_forward(y: torch.Tensor, w: torch.Tensor, target: torch.Tensor):
     lib = _lib.load()
     R, K = y.shape
     V = w.shape[0]
-    nt = (V + 255) // 256
+    nt = 2 * ((V + 255) // 256)  # two column halves per 256-wide vocabulary tile
     dev = y.device
     pm = torch.empty(nt, R, dtype=f32, device=dev)
     ps = torch.empty(nt, R, dtype=f32, device=dev)

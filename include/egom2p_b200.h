@@ -97,7 +97,8 @@ int egom2p_layernorm_bwd(const uint16_t* dy_bf16, const float* dy_f32, const flo
  *   a_mn = 0: A is (M,K) row-major (K contiguous);  a_mn = 1: A is stored (K,M) row-major (M contiguous)
  *   b_mn = 0: B is (N,K) row-major (K contiguous);  b_mn = 1: B is stored (K,N) row-major (N contiguous)
  * lda/ldb = row pitch in elements of the stored matrices. Epilogue: out = acc (+ bias[n]) (+ addend[m,n]);
- * written as bf16 (c_bf16) and/or fp32 (c_f32); addend may alias c_f32.
+ * written as bf16 (c_bf16) or fp32 (c_f32) -- exactly one; addend may alias c_f32 (accumulate). fp32 outputs with few
+ * tiles and long K (wgrad) are split along K and accumulated with TMA reduce-add.
  * ------------------------------------------------------------------------------------------------ */
 int egom2p_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, int64_t lda, int64_t ldb,
                      int32_t a_mn, int32_t b_mn, const float* bias, const float* addend, int64_t ld_add,
@@ -108,7 +109,7 @@ int egom2p_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N,
  * egom2p_model.py:614-644): logits = Y W^T are produced tile-by-tile in TMEM and never written to HBM.
  * ------------------------------------------------------------------------------------------------ */
 /* Pass 1: per (row, vocab tile) partial max / sum-exp and the target logit. part_* are (n_tiles, R) fp32 with
- * n_tiles = ceil(V / 256); tgt_logit (R) fp32 must be zero-initialised. */
+ * n_tiles = 2 * ceil(V / 256) (two column halves per 256-wide vocabulary tile); tgt_logit (R) fp32. */
 int egom2p_ce_partials(const uint16_t* Y, const uint16_t* W, const int64_t* target, int32_t R, int32_t V, int32_t K,
                        int64_t ldy, int64_t ldw, float* part_max, float* part_sum, float* tgt_logit, void* stream);
 /* Pass 2: lse[r] = logsumexp over tiles; loss_sum += sum_r (lse[r] - tgt_logit[r]) (one fp32, atomically). */
