@@ -42,9 +42,11 @@ SIGNATURES = {
     "egom2p_ce_finalize": [vp, vp, vp, i32, i32, vp, vp, vp],
     "egom2p_ce_dlogits": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, vp, i64, vp],
     "egom2p_attn_lse_stride": [i32],
-    "egom2p_attn_fwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp, vp, f32, vp, i64, vp, vp],
+    "egom2p_attn_ranges_bytes": [i32, i32],
+    "egom2p_attn_ranges": [vp, vp, i32, i32, i32, f32, vp, vp],
+    "egom2p_attn_fwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp, vp, i64, vp, vp],
     "egom2p_attn_bwd_scratch_bytes": [i32, i32, i32],
-    "egom2p_attn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, vp, f32, vp, vp, vp, vp,
+    "egom2p_attn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, f32, vp, vp, vp, vp,
                         i64, i64, i64, vp],
     "egom2p_swiglu_fwd": [vp, i64, i32, vp, vp],
     "egom2p_swiglu_bwd": [vp, vp, i64, i32, vp, vp],
@@ -56,7 +58,7 @@ SIGNATURES = {
     "egom2p_gather_rows_bf16": [vp, vp, i64, i32, vp, vp],
     "egom2p_scatter_rows_f32": [vp, vp, i64, i32, vp, vp],
 }
-_RESTYPES = {"egom2p_last_error": C.c_char_p, "egom2p_launch_count": i64, "egom2p_attn_bwd_scratch_bytes": i64}
+_RESTYPES = {"egom2p_last_error": C.c_char_p, "egom2p_launch_count": i64, "egom2p_attn_bwd_scratch_bytes": i64, "egom2p_attn_ranges_bytes": i64}
 
 _lib = None
 

@@ -1,138 +1,40 @@
-// Backward of the range-masked flash attention (see attn.cu for the tiling): three kernels.
-//   prep : delta = rowsum(dO * O), per-row effective key ranges / scales, per-64-row-block range summaries
-//   dQ   : per 128-query tile, loop over 64-key blocks: S, dP (TMEM) -> dS (smem) -> dQ += dS K (TMEM accumulator)
-//   dKV  : per 128-key tile, loop over the 64-query blocks that can see it: S^T, dP^T (TMEM) -> P^T, dS^T (smem)
-//          -> dV += P^T dO, dK += dS^T Q (TMEM accumulators). No atomics, deterministic.
-#include <climits>
-
-#include "common.cuh"
+// Backward of the range-masked flash attention (see attn.cu for the tiling and attn_common.cuh for the range metadata).
+//   dQ  : per 128-query tile, loop over 64-key blocks: S, dP (TMEM) -> dS (smem) -> dQ += dS K (TMEM accumulator).
+//         Also computes delta = rowsum(dO * O) for its rows and leaves -delta*scale in scratch for the dKV kernel.
+//   dKV : per 128-key tile, loop over the 64-query blocks that can see it: S^T, dP^T (TMEM) -> P^T, dS^T (smem)
+//         -> dV += P^T dO, dK += dS^T Q (TMEM accumulators). No atomics, deterministic.
+// Both kernels use 8 math warps (two per TMEM lane quarter, 32 columns each) + TMA warp + MMA warp, 2 CTAs per SM.
+#include "attn_common.cuh"
 
 namespace egom2p {
-
-constexpr int kThreads = 192;
-constexpr int kD = 64;
-constexpr int kT = 128;   // tile rows (queries in dQ, keys in dKV)
-constexpr int kBlk = 64;  // inner block
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
-  return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-struct Scratch {
-  float* delta;      // (B, H, S)   -delta * rs_nat  (pre-folded for  dS = P * fma(dP, rs_nat, .))
-  float* nlse;       // (B, H, S)   -lse2
-  int32_t* blk_lo_max;  // (B, S/64)  max row lo  (INT_MAX if the block holds a uniform / padding row)
-  int32_t* blk_hi_min;  // (B, S/64)  min row hi
-  int32_t* row_lo;   // (B, S)
-  int32_t* row_hi;   // (B, S)
-  float* row_scale;  // (B, S)  scale*log2e, or 0 for fully-masked (uniform) rows
-  int32_t* blk_lo;   // (B, S/64)
-  int32_t* blk_hi;   // (B, S/64)
-};
-static inline int pad64(int x) { return (x + 63) / 64 * 64; }
-static inline Scratch carve(void* base, int B, int H, int Mq) {
-  const int64_t S = pad64(Mq);
-  Scratch s;
-  char* p = reinterpret_cast<char*>(base);
-  s.delta = reinterpret_cast<float*>(p); p += (int64_t)B * H * S * 4;
-  s.nlse = reinterpret_cast<float*>(p); p += (int64_t)B * H * S * 4;
-  s.blk_lo_max = reinterpret_cast<int32_t*>(p); p += (int64_t)B * (S / 64) * 4 + 192;
-  p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
-  s.blk_hi_min = reinterpret_cast<int32_t*>(p); p += (int64_t)B * (S / 64) * 4 + 192;
-  p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
-  s.row_lo = reinterpret_cast<int32_t*>(p); p += (int64_t)B * S * 4;
-  s.row_hi = reinterpret_cast<int32_t*>(p); p += (int64_t)B * S * 4;
-  s.row_scale = reinterpret_cast<float*>(p); p += (int64_t)B * S * 4;
-  s.blk_lo = reinterpret_cast<int32_t*>(p); p += (int64_t)B * (S / 64) * 4;
-  s.blk_hi = reinterpret_cast<int32_t*>(p);
-  return s;
-}
-
-// ------------------------------------------------------------------------------------------------ prep
-__global__ void __launch_bounds__(256) attn_prep_kernel(const uint16_t* __restrict__ O, const uint16_t* __restrict__ dO,
-                                                        int64_t ldo, int B, int H, int Mq, int Nk, int S,
-                                                        const int32_t* __restrict__ key_lo, const int32_t* __restrict__ key_hi,
-                                                        const float* __restrict__ lse2, float scale_log2, Scratch sc) {
-  const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per (b, padded row)
-  if (gw >= (int64_t)B * S) return;
-  const int lane = threadIdx.x & 31;
-  const int b = (int)(gw / S), r = (int)(gw % S);
-  if (r >= Mq) {
-    if (lane == 0) { sc.row_lo[gw] = INT_MAX / 2; sc.row_hi[gw] = 0; sc.row_scale[gw] = 0.f; }
-    for (int h = lane; h < H; h += 32) {
-      sc.delta[((int64_t)b * H + h) * S + r] = 0.f;
-      sc.nlse[((int64_t)b * H + h) * S + r] = -INFINITY;
-    }
-    return;
-  }
-  int lo = key_lo ? key_lo[(int64_t)b * Mq + r] : 0;
-  int hi = key_hi ? key_hi[(int64_t)b * Mq + r] : Nk;
-  lo = max(lo, 0); hi = min(hi, Nk);
-  float rs = scale_log2;
-  if (hi <= lo) { lo = 0; hi = Nk; rs = 0.f; }
-  if (lane == 0) { sc.row_lo[gw] = lo; sc.row_hi[gw] = hi; sc.row_scale[gw] = rs; }
-  const uint32_t* o = reinterpret_cast<const uint32_t*>(O + ((int64_t)b * Mq + r) * ldo);
-  const uint32_t* d = reinterpret_cast<const uint32_t*>(dO + ((int64_t)b * Mq + r) * ldo);
-  for (int h = 0; h < H; ++h) {
-    const uint32_t a = o[h * 32 + lane], g = d[h * 32 + lane];
-    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a));
-    const float2 fg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g));
-    const float s = warp_sum(fa.x * fg.x + fa.y * fg.y);
-    if (lane == 0) {
-      sc.delta[((int64_t)b * H + h) * S + r] = -s * (rs * kLn2);
-      sc.nlse[((int64_t)b * H + h) * S + r] = -lse2[((int64_t)b * H + h) * S + r];
-    }
-  }
-}
-__global__ void attn_blk_kernel(int B, int S, Scratch sc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * (S / 64)) return;
-  int lo = INT_MAX, hi = INT_MIN, lo_max = INT_MIN, hi_min = INT_MAX;
-  for (int r = 0; r < 64; ++r) {
-    const int l = sc.row_lo[(int64_t)i * 64 + r], h = sc.row_hi[(int64_t)i * 64 + r];
-    if (h > l) { lo = min(lo, l); hi = max(hi, h); }
-    const bool normal = (h > l) && sc.row_scale[(int64_t)i * 64 + r] != 0.f;
-    lo_max = normal ? max(lo_max, l) : INT_MAX;
-    hi_min = normal ? min(hi_min, h) : INT_MIN;
-  }
-  sc.blk_lo[i] = lo;
-  sc.blk_hi[i] = hi;
-  sc.blk_lo_max[i] = lo_max;
-  sc.blk_hi_min[i] = hi_min;
-}
 
 // ------------------------------------------------------------------------------------------------ dQ
 struct DqParams {
   int B, H, Mq, Nk, S;
-  Scratch sc;
+  RangeMeta meta;
+  const float* lse2;     // (B, H, S)
+  const uint16_t* O;
+  const uint16_t* dO;
+  int64_t ldo;
+  float* ndelta;         // (B, H, S) out: -delta * scale (natural-log units), consumed by the dKV kernel
   uint16_t* dQ;
   int64_t lddq;
 };
 constexpr int kDqStages = 3;
 struct DqSmem {
   static constexpr int kQ = 0, kDO = kQ + kT * 128, kK = kDO + kT * 128, kV = kK + kDqStages * kBlk * 128,
-                       kDS = kV + kDqStages * kBlk * 128, kBar = kDS + kT * 128, kTotal = kBar + 256 + 1024;
+                       kDS = kV + kDqStages * kBlk * 128, kX = kDS + kT * 128, kBar = kX + 2 * kT * 4,
+                       kTotal = kBar + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const DqParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sQ = smem + DqSmem::kQ, *sDO = smem + DqSmem::kDO, *sK = smem + DqSmem::kK, *sV = smem + DqSmem::kV,
           *sDS = smem + DqSmem::kDS;
+  float* sX = reinterpret_cast<float*>(smem + DqSmem::kX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqSmem::kBar);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
@@ -145,30 +47,32 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_full + 1);
   int* s_range = reinterpret_cast<int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
-  if (tid == 0) {
+  const int quarter = warp & 3, half = (warp >> 2) & 1;
+  const int trow = quarter * 32 + lane;
+  const int row = q0 + trow;
+  if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < kDqStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 128);
-    mbar_init(ds_full, 128);
+    mbar_init(sdp_free, 32 * kAttnComputeWarps);
+    mbar_init(ds_full, 32 * kAttnComputeWarps);
     mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);
     fence_mbar_init();
     s_range[0] = INT_MAX;
     s_range[1] = INT_MIN;
   }
-  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<256>(tmem_slot);
   __syncthreads();
-  const int row = q0 + tid;
   int lo = INT_MAX, hi = INT_MIN;
   float rscale = 0.f;
-  if (warp < 4 && row < p.Mq) {
-    lo = p.sc.row_lo[(int64_t)b * p.S + row];
-    hi = p.sc.row_hi[(int64_t)b * p.S + row];
-    rscale = p.sc.row_scale[(int64_t)b * p.S + row];
-    if (hi > lo) { atomicMin(&s_range[0], lo); atomicMax(&s_range[1], hi); }
+  if (warp < kAttnComputeWarps && row < p.Mq) {
+    lo = p.meta.row_lo[(int64_t)b * p.S + row];
+    hi = p.meta.row_hi[(int64_t)b * p.S + row];
+    rscale = p.meta.row_scale[(int64_t)b * p.S + row];
+    if (half == 0 && hi > lo) { atomicMin(&s_range[0], lo); atomicMax(&s_range[1], hi); }
   }
   tc_fence_before();
   __syncthreads();
@@ -177,7 +81,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int lo_cta = s_range[0], hi_cta = s_range[1];
   const int nblk = hi_cta > lo_cta ? (hi_cta - lo_cta + kBlk - 1) / kBlk : 0;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     if (lane == 0 && nblk > 0) {
       mbar_expect_tx(q_full, 2 * kT * 128);
       tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
@@ -191,7 +95,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_2d(sV + st * kBlk * 128, &tmV, &kv_full[st], h * kD, krow);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0 && nblk > 0) {
       constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBlk, 0, 0);
       constexpr uint32_t idesc_kmn = umma_idesc_bf16(128, kD, 0, 1);
@@ -233,81 +137,92 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       umma_commit(dq_full);
     }
   } else {
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float nlse = -INFINITY, ndelta = 0.f;   // -lse2 and -delta * rs_nat
-    if (row < p.Mq) {
-      nlse = p.sc.nlse[((int64_t)b * p.H + h) * p.S + row];
-      ndelta = p.sc.delta[((int64_t)b * p.H + h) * p.S + row];
-    }
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;
     const float rs_nat = rscale * kLn2;
+    // delta = sum_d dO * O over the row (two halves combined through smem)
+    float part = 0.f, nlse = -INFINITY;
+    if (row < p.Mq) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.O + ((int64_t)b * p.Mq + row) * p.ldo + h * kD + half * 32);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dO + ((int64_t)b * p.Mq + row) * p.ldo + h * kD + half * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = po[i], g = pd[i];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[u]));
+          const float2 fg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[u]));
+          part += fa.x * fg.x + fa.y * fg.y;
+        }
+      }
+      nlse = -p.lse2[((int64_t)b * p.H + h) * p.S + row];
+    }
+    sX[half * kT + trow] = part;
+    pair_sync(quarter);
+    const float ndelta = -(part + sX[(half ^ 1) * kT + trow]) * rs_nat;
+    if (half == 0 && row < p.S) p.ndelta[((int64_t)b * p.H + h) * p.S + row] = row < p.Mq ? ndelta : 0.f;
+
     for (int j = 0; j < nblk; ++j) {
-      const int kv0 = lo_cta + j * kBlk;
+      const int kv0 = lo_cta + j * kBlk + half * 32;
       mbar_wait(sdp_full, j & 1);
       tc_fence_after();
-      uint32_t s0[32], s1[32], d0[32], d1[32];
-      tmem_ld32(tmem_base + lane_addr, s0);
-      tmem_ld32(tmem_base + lane_addr + 32, s1);
-      tmem_ld32(tmem_base + lane_addr + 64, d0);
-      tmem_ld32(tmem_base + lane_addr + 96, d1);
+      uint32_t s[32], d[32];
+      tmem_ld32(t_lane, s);
+      tmem_ld32(t_lane + 64, d);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(sdp_free);
       float sc = rscale;
-      if (!(rscale != 0.f && kv0 >= lo && kv0 + kBlk <= hi)) {
+      if (!(rscale != 0.f && kv0 >= lo && kv0 + 32 <= hi)) {
         sc = rscale != 0.f ? rscale : 1.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const bool ok0 = (kv0 + c >= lo) && (kv0 + c < hi), ok1 = (kv0 + 32 + c >= lo) && (kv0 + 32 + c < hi);
-          s0[c] = ok0 ? (rscale != 0.f ? s0[c] : 0u) : 0xff800000u;
-          s1[c] = ok1 ? (rscale != 0.f ? s1[c] : 0u) : 0xff800000u;
+          const bool ok = (kv0 + c >= lo) && (kv0 + c < hi);
+          s[c] = ok ? (rscale != 0.f ? s[c] : 0u) : 0xff800000u;
         }
       }
       if (j > 0) mbar_wait(ds_empty, (j - 1) & 1);
 #pragma unroll
-      for (int c8 = 0; c8 < kBlk / 8; ++c8) {
+      for (int c8 = 0; c8 < 4; ++c8) {
         float e[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int c = c8 * 8 + u;
-          const float s = __uint_as_float(c < 32 ? s0[c] : s1[c - 32]);
-          const float dp = __uint_as_float(c < 32 ? d0[c] : d1[c - 32]);
-          e[u] = ex2(fmaf(s, sc, nlse)) * fmaf(dp, rs_nat, ndelta);
+          e[u] = ex2(fmaf(__uint_as_float(s[c]), sc, nlse)) * fmaf(__uint_as_float(d[c]), rs_nat, ndelta);
         }
         uint4 pk;
         pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
-        *reinterpret_cast<uint4*>(sDS + swz_off(tid, c8)) = pk;
+        *reinterpret_cast<uint4*>(sDS + swz_off(trow, half * 4 + c8)) = pk;
       }
       fence_async_smem();
       mbar_arrive(ds_full);
     }
-    uint32_t v0[32], v1[32];
+    uint32_t v[32];
     if (nblk > 0) {
       mbar_wait(dq_full, 0);
       tc_fence_after();
-      tmem_ld32(tmem_base + lane_addr + 128, v0);
-      tmem_ld32(tmem_base + lane_addr + 160, v1);
+      tmem_ld32(t_lane + 128, v);
       tmem_ld_wait();
     } else {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) { v0[c] = 0u; v1[c] = 0u; }
+      for (int c = 0; c < 32; ++c) v[c] = 0u;
     }
     if (row < p.Mq) {
-      uint16_t* out = p.dQ + ((int64_t)b * p.Mq + row) * p.lddq + h * kD;
+      uint16_t* out = p.dQ + ((int64_t)b * p.Mq + row) * p.lddq + h * kD + half * 32;
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        const uint32_t* src = c8 < 4 ? &v0[c8 * 8] : &v1[(c8 - 4) * 8];
+      for (int c8 = 0; c8 < 4; ++c8) {
         uint4 pk;
-        pk.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
-        pk.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
-        pk.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
-        pk.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+        pk.x = pack_bf16(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
+        pk.y = pack_bf16(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
+        pk.z = pack_bf16(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
+        pk.w = pack_bf16(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
         reinterpret_cast<uint4*>(out)[c8] = pk;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
   }
@@ -317,13 +232,15 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 struct DkvParams {
   int B, H, Mq, Nk, S;
   float scale_log2;
-  Scratch sc;
+  RangeMeta meta;
+  const float* lse2;
+  const float* ndelta;
   uint16_t* dK;
   uint16_t* dV;
   int64_t lddk, lddv;
 };
 constexpr int kDkvStages = 2;
-constexpr int kMetaBytes = 5 * kBlk * 4;  // -lse2, -delta*rs, lo, hi, scale for 64 query rows
+constexpr int kMetaBytes = 5 * kBlk * 4;  // lse2, -delta*scale, lo, hi, row scale for 64 query rows
 constexpr int kMaxQBlocks = 1024;
 struct DkvSmem {
   static constexpr int kK = 0, kV = kK + kT * 128, kQ = kV + kT * 128, kDO = kQ + kDkvStages * kBlk * 128,
@@ -331,7 +248,7 @@ struct DkvSmem {
                        kList = kMeta + kDkvStages * kMetaBytes, kBar = kList + kMaxQBlocks * 2, kTotal = kBar + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const DkvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -351,37 +268,46 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
   int* s_n = reinterpret_cast<int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
+  const int quarter = warp & 3, half = (warp >> 2) & 1;
+  const int trow = quarter * 32 + lane;
   const int nqb = p.S / kBlk;
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < kDkvStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 128);
-    mbar_init(pds_full, 128);
+    mbar_init(sdp_free, 32 * kAttnComputeWarps);
+    mbar_init(pds_full, 32 * kAttnComputeWarps);
     mbar_init(pds_empty, 1);
     mbar_init(dkv_full, 1);
     fence_mbar_init();
-    int n = 0;  // query blocks whose key ranges intersect this key tile
-    for (int i = 0; i < nqb; ++i) {
-      const int64_t o = (int64_t)b * nqb + i;
-      const int bl = p.sc.blk_lo[o], bh = p.sc.blk_hi[o];
-      if (bh > kv0 && bl < kv0 + kT && n < kMaxQBlocks) {
-        const bool inside = p.sc.blk_lo_max[o] <= kv0 && p.sc.blk_hi_min[o] >= kv0 + kT;
-        s_list[n++] = (uint16_t)(i | (inside ? 0x8000 : 0));
-      }
-    }
-    *s_n = n;
   }
-  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  if (warp == 0) {  // query blocks whose key ranges intersect this key tile (ballot-compacted, ascending)
+    int n = 0;
+    for (int i0 = 0; i0 < nqb; i0 += 32) {
+      const int i = i0 + lane;
+      bool take = false, inside = false;
+      if (i < nqb) {
+        const int64_t o = (int64_t)b * nqb + i;
+        take = p.meta.blk_hi[o] > kv0 && p.meta.blk_lo[o] < kv0 + kT;
+        inside = p.meta.blk_lo_max[o] <= kv0 && p.meta.blk_hi_min[o] >= kv0 + kT;
+      }
+      const unsigned msk = __ballot_sync(0xffffffffu, take);
+      const int pos = n + __popc(msk & ((1u << lane) - 1));
+      if (take && pos < kMaxQBlocks) s_list[pos] = (uint16_t)(i | (inside ? 0x8000 : 0));
+      n += __popc(msk);
+    }
+    if (lane == 0) *s_n = n < kMaxQBlocks ? n : kMaxQBlocks;
+  }
+  if (warp == kMmaWarp) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n = *s_n;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     if (lane == 0 && n > 0) {
       mbar_expect_tx(kv_full, 2 * kT * 128);
       tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
@@ -395,14 +321,14 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_2d(sDO + st * kBlk * 128, &tmDO, &q_full[st], h * kD, b * p.Mq + r0);
         uint8_t* meta = sMeta + st * kMetaBytes;
         const int64_t hoff = ((int64_t)b * p.H + h) * p.S + r0, roff = (int64_t)b * p.S + r0;
-        bulk_load(meta + 0 * 256, p.sc.nlse + hoff, 256, &q_full[st]);
-        bulk_load(meta + 1 * 256, p.sc.delta + hoff, 256, &q_full[st]);
-        bulk_load(meta + 2 * 256, p.sc.row_lo + roff, 256, &q_full[st]);
-        bulk_load(meta + 3 * 256, p.sc.row_hi + roff, 256, &q_full[st]);
-        bulk_load(meta + 4 * 256, p.sc.row_scale + roff, 256, &q_full[st]);
+        bulk_load(meta + 0 * 256, p.lse2 + hoff, 256, &q_full[st]);
+        bulk_load(meta + 1 * 256, p.ndelta + hoff, 256, &q_full[st]);
+        bulk_load(meta + 2 * 256, p.meta.row_lo + roff, 256, &q_full[st]);
+        bulk_load(meta + 3 * 256, p.meta.row_hi + roff, 256, &q_full[st]);
+        bulk_load(meta + 4 * 256, p.meta.row_scale + roff, 256, &q_full[st]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0 && n > 0) {
       constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBlk, 0, 0);
       constexpr uint32_t idesc_kmn = umma_idesc_bf16(128, kD, 0, 1);
@@ -448,8 +374,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(dkv_full);
     }
   } else {
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const int kidx = kv0 + tid;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;
+    const int kidx = kv0 + trow;
     const float SC = p.scale_log2, RN = p.scale_log2 * kLn2;
     for (int idx = 0; idx < n; ++idx) {
       const int st = idx % kDkvStages;
@@ -457,16 +383,14 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&q_full[st], (idx / kDkvStages) & 1);  // row metadata visible
       mbar_wait(sdp_full, idx & 1);
       tc_fence_after();
-      const float* m_nl = reinterpret_cast<const float*>(sMeta + st * kMetaBytes);
-      const float* m_nd = m_nl + 64;
-      const int* m_lo = reinterpret_cast<const int*>(m_nl + 128);
+      const float* m_ls = reinterpret_cast<const float*>(sMeta + st * kMetaBytes) + half * 32;  // this thread's 32 query rows
+      const float* m_nd = m_ls + 64;
+      const int* m_lo = reinterpret_cast<const int*>(m_ls + 128);
       const int* m_hi = m_lo + 64;
-      const float* m_rs = m_nl + 256;
-      uint32_t s0[32], s1[32], d0[32], d1[32];
-      tmem_ld32(tmem_base + lane_addr, s0);
-      tmem_ld32(tmem_base + lane_addr + 32, s1);
-      tmem_ld32(tmem_base + lane_addr + 64, d0);
-      tmem_ld32(tmem_base + lane_addr + 96, d1);
+      const float* m_rs = m_ls + 256;
+      uint32_t s[32], d[32];
+      tmem_ld32(t_lane, s);
+      tmem_ld32(t_lane + 64, d);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(sdp_free);
@@ -474,45 +398,41 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (inside) {
         // every (key, query) pair of this block is unmasked and every row uses the plain scale
 #pragma unroll
-        for (int c8 = 0; c8 < kBlk / 8; ++c8) {
-          const float4 nl0 = *reinterpret_cast<const float4*>(m_nl + c8 * 8), nl1 = *reinterpret_cast<const float4*>(m_nl + c8 * 8 + 4);
-          const float4 nd0 = *reinterpret_cast<const float4*>(m_nd + c8 * 8), nd1 = *reinterpret_cast<const float4*>(m_nd + c8 * 8 + 4);
-          const float nl[8] = {nl0.x, nl0.y, nl0.z, nl0.w, nl1.x, nl1.y, nl1.z, nl1.w};
-          const float nd[8] = {nd0.x, nd0.y, nd0.z, nd0.w, nd1.x, nd1.y, nd1.z, nd1.w};
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const float4 l0 = *reinterpret_cast<const float4*>(m_ls + c8 * 8), l1 = *reinterpret_cast<const float4*>(m_ls + c8 * 8 + 4);
+          const float4 n0 = *reinterpret_cast<const float4*>(m_nd + c8 * 8), n1 = *reinterpret_cast<const float4*>(m_nd + c8 * 8 + 4);
+          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float nd[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
           float pt[8], e[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int c = c8 * 8 + u;
-            const float s = __uint_as_float(c < 32 ? s0[c] : s1[c - 32]);
-            const float dp = __uint_as_float(c < 32 ? d0[c] : d1[c - 32]);
-            pt[u] = ex2(fmaf(s, SC, nl[u]));
-            e[u] = pt[u] * fmaf(dp, RN, nd[u]);
+            pt[u] = ex2(fmaf(__uint_as_float(s[c]), SC, -ls[u]));
+            e[u] = pt[u] * fmaf(__uint_as_float(d[c]), RN, nd[u]);
           }
           uint4 pk;
           pk.x = pack_bf16(pt[0], pt[1]); pk.y = pack_bf16(pt[2], pt[3]); pk.z = pack_bf16(pt[4], pt[5]); pk.w = pack_bf16(pt[6], pt[7]);
-          *reinterpret_cast<uint4*>(sPT + swz_off(tid, c8)) = pk;
+          *reinterpret_cast<uint4*>(sPT + swz_off(trow, half * 4 + c8)) = pk;
           pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
-          *reinterpret_cast<uint4*>(sDST + swz_off(tid, c8)) = pk;
+          *reinterpret_cast<uint4*>(sDST + swz_off(trow, half * 4 + c8)) = pk;
         }
       } else {
 #pragma unroll
-        for (int c8 = 0; c8 < kBlk / 8; ++c8) {
+        for (int c8 = 0; c8 < 4; ++c8) {
           float pt[8], e[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int c = c8 * 8 + u;
-            const float s = __uint_as_float(c < 32 ? s0[c] : s1[c - 32]);
-            const float dp = __uint_as_float(c < 32 ? d0[c] : d1[c - 32]);
             const float rs = m_rs[c];
             const bool ok = kidx >= m_lo[c] && kidx < m_hi[c];
-            pt[u] = ok ? ex2(fmaf(rs != 0.f ? s : 0.f, rs, m_nl[c])) : 0.f;
-            e[u] = pt[u] * fmaf(dp, rs * kLn2, m_nd[c]);
+            pt[u] = ok ? ex2(fmaf(rs != 0.f ? __uint_as_float(s[c]) : 0.f, rs, -m_ls[c])) : 0.f;
+            e[u] = pt[u] * fmaf(__uint_as_float(d[c]), rs * kLn2, m_nd[c]);
           }
           uint4 pk;
           pk.x = pack_bf16(pt[0], pt[1]); pk.y = pack_bf16(pt[2], pt[3]); pk.z = pack_bf16(pt[4], pt[5]); pk.w = pack_bf16(pt[6], pt[7]);
-          *reinterpret_cast<uint4*>(sPT + swz_off(tid, c8)) = pk;
+          *reinterpret_cast<uint4*>(sPT + swz_off(trow, half * 4 + c8)) = pk;
           pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
-          *reinterpret_cast<uint4*>(sDST + swz_off(tid, c8)) = pk;
+          *reinterpret_cast<uint4*>(sDST + swz_off(trow, half * 4 + c8)) = pk;
         }
       }
       fence_async_smem();
@@ -523,27 +443,25 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
     }
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {  // 0: dV (cols 128..191), 1: dK (cols 192..255)
-      uint32_t v0[32], v1[32];
+    for (int which = 0; which < 2; ++which) {  // 0: dV (cols 128..191), 1: dK (cols 192..255); this thread: 32 of the 64 columns
+      uint32_t v[32];
       if (n > 0) {
-        tmem_ld32(tmem_base + lane_addr + 128 + which * 64, v0);
-        tmem_ld32(tmem_base + lane_addr + 160 + which * 64, v1);
+        tmem_ld32(t_lane + 128 + which * 64, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { v0[c] = 0u; v1[c] = 0u; }
+        for (int c = 0; c < 32; ++c) v[c] = 0u;
       }
       if (kidx < p.Nk) {
-        uint16_t* out = which == 0 ? p.dV + ((int64_t)b * p.Nk + kidx) * p.lddv + h * kD
-                                   : p.dK + ((int64_t)b * p.Nk + kidx) * p.lddk + h * kD;
+        uint16_t* out = (which == 0 ? p.dV + ((int64_t)b * p.Nk + kidx) * p.lddv : p.dK + ((int64_t)b * p.Nk + kidx) * p.lddk) +
+                        h * kD + half * 32;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const uint32_t* src = c8 < 4 ? &v0[c8 * 8] : &v1[(c8 - 4) * 8];
+        for (int c8 = 0; c8 < 4; ++c8) {
           uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
-          pk.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
-          pk.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
-          pk.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+          pk.x = pack_bf16(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
+          pk.y = pack_bf16(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
+          pk.z = pack_bf16(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
+          pk.w = pack_bf16(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
           reinterpret_cast<uint4*>(out)[c8] = pk;
         }
       }
@@ -551,7 +469,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
   }
@@ -560,29 +478,23 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace egom2p
 
 extern "C" int64_t egom2p_attn_bwd_scratch_bytes(int32_t B, int32_t H, int32_t Mq) {
-  const int64_t S = egom2p::pad64(Mq);
-  return 2 * (int64_t)B * H * S * 4 + 3 * (int64_t)B * S * 4 + 4 * ((int64_t)B * (S / 64) * 4 + 512) + 1024;
+  return (int64_t)B * H * egom2p::pad64(Mq) * 4 + 256;
 }
 
 extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, const uint16_t* O, const uint16_t* dO,
                                const float* lse, int32_t B, int32_t H, int32_t Mq, int32_t Nk, int64_t ldq, int64_t ldk,
-                               int64_t ldv, int64_t ldo, const int32_t* key_lo, const int32_t* key_hi, float scale,
-                               void* scratch, uint16_t* dQ, uint16_t* dK, uint16_t* dV, int64_t lddq, int64_t lddk,
-                               int64_t lddv, void* stream_) {
+                               int64_t ldv, int64_t ldo, const void* meta, float scale, void* scratch, uint16_t* dQ,
+                               uint16_t* dK, uint16_t* dV, int64_t lddq, int64_t lddk, int64_t lddv, void* stream_) {
   using namespace egom2p;
   cudaStream_t stream = (cudaStream_t)stream_;
-  EGO_REQUIRE(Q && O && dO && lse && scratch && dQ && B > 0 && H > 0 && Mq > 0 && Nk >= 0, "attn_bwd: bad argument");
-  EGO_REQUIRE((key_lo == nullptr) == (key_hi == nullptr), "attn_bwd: key_lo / key_hi must both be given or both NULL");
-  EGO_REQUIRE(((uintptr_t)scratch & 255) == 0, "attn_bwd: scratch must be 256-byte aligned");
-  EGO_REQUIRE(lddq % 8 == 0 && ((uintptr_t)dQ & 15) == 0, "attn_bwd: dQ alignment");
+  EGO_REQUIRE(Q && O && dO && lse && meta && scratch && dQ && B > 0 && H > 0 && Mq > 0 && Nk >= 0, "attn_bwd: bad argument");
+  EGO_REQUIRE(((uintptr_t)scratch & 255) == 0 && ((uintptr_t)lse & 255) == 0 && ((uintptr_t)meta & 255) == 0,
+              "attn_bwd: scratch / lse / meta must be 256-byte aligned");
+  EGO_REQUIRE(lddq % 8 == 0 && ((uintptr_t)dQ & 15) == 0 && ldo % 8 == 0 && ((uintptr_t)O & 15) == 0 && ((uintptr_t)dO & 15) == 0,
+              "attn_bwd: dQ / O / dO alignment");
   const int S = pad64(Mq);
-  Scratch sc = carve(scratch, B, H, Mq);
-  attn_prep_kernel<<<(unsigned)(((int64_t)B * S + 7) / 8), 256, 0, stream>>>(O, dO, ldo, B, H, Mq, Nk, S, key_lo, key_hi, lse,
-                                                                          scale * kLog2e, sc);
-  int rc = check_launch("attn_bwd prep");
-  if (rc) return rc;
-  attn_blk_kernel<<<(B * (S / 64) + 127) / 128, 128, 0, stream>>>(B, S, sc);
-  if ((rc = check_launch("attn_bwd blk"))) return rc;
+  RangeMeta rm = carve_meta(const_cast<void*>(meta), B, Mq);
+  float* ndelta = reinterpret_cast<float*>(scratch);
 
   CUtensorMap tmQ, tmDO, tmK, tmV;
   static bool attr_set = false;
@@ -592,7 +504,8 @@ extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint1
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_bwd: cudaFuncSetAttribute failed"); return EGOM2P_ERR_CUDA; }
     attr_set = true;
   }
-  // ---- dQ
+  int rc;
+  // ---- dQ (+ delta)
   if ((rc = make_tmap_bf16_2d(&tmQ, Q, (uint64_t)B * Mq, (uint64_t)H * kD, ldq, kT, kD))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmDO, dO, (uint64_t)B * Mq, (uint64_t)H * kD, ldo, kT, kD))) return rc;
   if (Nk > 0) {
@@ -602,8 +515,8 @@ extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint1
   } else {
     tmK = tmQ; tmV = tmQ;
   }
-  DqParams pq{B, H, Mq, Nk, S, sc, dQ, lddq};
-  attn_dq_kernel<<<dim3((Mq + kT - 1) / kT, H, B), kThreads, DqSmem::kTotal, stream>>>(tmQ, tmDO, tmK, tmV, pq);
+  DqParams pq{B, H, Mq, Nk, S, rm, lse, O, dO, ldo, ndelta, dQ, lddq};
+  attn_dq_kernel<<<dim3(S / kT + (S % kT ? 1 : 0), H, B), kAttnThreads, DqSmem::kTotal, stream>>>(tmQ, tmDO, tmK, tmV, pq);
   if ((rc = check_launch("attn_bwd dq"))) return rc;
   if (Nk == 0) return EGOM2P_OK;
   // ---- dK / dV
@@ -613,7 +526,7 @@ extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint1
   if ((rc = make_tmap_bf16_2d(&tmDO, dO, (uint64_t)B * Mq, (uint64_t)H * kD, ldo, kBlk, kD))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmK, K, (uint64_t)B * Nk, (uint64_t)H * kD, ldk, kT, kD))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmV, V, (uint64_t)B * Nk, (uint64_t)H * kD, ldv, kT, kD))) return rc;
-  DkvParams pk{B, H, Mq, Nk, S, scale * kLog2e, sc, dK, dV, lddk, lddv};
-  attn_dkv_kernel<<<dim3((Nk + kT - 1) / kT, H, B), kThreads, DkvSmem::kTotal, stream>>>(tmQ, tmDO, tmK, tmV, pk);
+  DkvParams pk{B, H, Mq, Nk, S, scale * kLog2e, rm, lse, ndelta, dK, dV, lddk, lddv};
+  attn_dkv_kernel<<<dim3((Nk + kT - 1) / kT, H, B), kAttnThreads, DkvSmem::kTotal, stream>>>(tmQ, tmDO, tmK, tmV, pk);
   return check_launch("attn_bwd dkv");
 }

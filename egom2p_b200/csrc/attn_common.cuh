@@ -1,0 +1,72 @@
+// Shared pieces of the attention kernels: tiling constants, range metadata layout, small device helpers.
+#pragma once
+#include <climits>
+
+#include "common.cuh"
+
+namespace egom2p {
+
+constexpr int kAttnComputeWarps = 8;                       // two warps per TMEM lane quarter (column halves)
+constexpr int kAttnThreads = 32 * (kAttnComputeWarps + 2); // + TMA warp + MMA warp
+constexpr int kTmaWarp = kAttnComputeWarps, kMmaWarp = kAttnComputeWarps + 1;
+constexpr int kD = 64;     // head dim
+constexpr int kT = 128;    // tile rows (queries in fwd / dQ, keys in dKV)
+constexpr int kBlk = 64;   // inner block (keys in fwd / dQ, query rows in dKV)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2 (exp2f adds range fix-ups the softmax does not need)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) {  // 16-byte chunk in a [rows][128 B] SW128 tile
+  return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void pair_sync(int quarter) {  // the two warps that share a TMEM lane quarter
+  switch (quarter) {  // immediate barrier ids keep the CTA at 5 named barriers instead of reserving all 16
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+// Range metadata of one (plan, attention kind): built once per forward by egom2p_attn_ranges, shared by all layers,
+// heads and by forward + backward. S = Mq rounded up to 64.
+struct RangeMeta {
+  int32_t* row_lo;      // (B, S) effective key range per query row; rows >= Mq: empty
+  int32_t* row_hi;      // (B, S)
+  float* row_scale;     // (B, S) scale*log2e, or 0 for fully-masked rows (uniform attention over all keys)
+  int32_t* blk_lo;      // (B, S/64) union of the rows' ranges per 64-row block
+  int32_t* blk_hi;
+  int32_t* blk_lo_max;  // (B, S/64) intersection (INT_MAX / INT_MIN if the block holds a uniform or padding row)
+  int32_t* blk_hi_min;
+};
+static inline int pad64(int x) { return (x + 63) / 64 * 64; }
+static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+static inline int64_t range_meta_bytes(int B, int Mq) {
+  const int64_t S = pad64(Mq);
+  return 3 * align256((int64_t)B * S * 4) + 4 * align256((int64_t)B * (S / 64) * 4);
+}
+static inline RangeMeta carve_meta(void* base, int B, int Mq) {
+  const int64_t S = pad64(Mq);
+  const int64_t rows = align256((int64_t)B * S * 4), blks = align256((int64_t)B * (S / 64) * 4);
+  char* p = reinterpret_cast<char*>(base);
+  RangeMeta m;
+  m.row_lo = reinterpret_cast<int32_t*>(p); p += rows;
+  m.row_hi = reinterpret_cast<int32_t*>(p); p += rows;
+  m.row_scale = reinterpret_cast<float*>(p); p += rows;
+  m.blk_lo = reinterpret_cast<int32_t*>(p); p += blks;
+  m.blk_hi = reinterpret_cast<int32_t*>(p); p += blks;
+  m.blk_lo_max = reinterpret_cast<int32_t*>(p); p += blks;
+  m.blk_hi_min = reinterpret_cast<int32_t*>(p);
+  return m;
+}
+
+}  // namespace egom2p

@@ -65,13 +65,31 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w ; dw += sum_rows dy * xhat.
 // Each warp walks rows [row0 + warp, ...) with stride 8 inside its CTA's row chunk and keeps per-lane dw partials.
+// Only the raw x / dy registers stay live across the two warp reductions (xhat and g are recomputed), which keeps the
+// kernel at <= 80 registers -> 3 CTAs (24 warps) per SM to cover the load -> reduce -> store latency chain.
+template <bool kBf16> struct DyVec;
+template <> struct DyVec<true> {
+  uint2 raw;
+  __device__ __forceinline__ void load(const void* p, int64_t off4) { raw = reinterpret_cast<const uint2*>(p)[off4]; }
+  __device__ __forceinline__ float4 get() const {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+template <> struct DyVec<false> {
+  float4 raw;
+  __device__ __forceinline__ void load(const void* p, int64_t off4) { raw = reinterpret_cast<const float4*>(p)[off4]; }
+  __device__ __forceinline__ float4 get() const { return raw; }
+};
+
 template <bool kDyBf16, int NV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
-                                                     const float* __restrict__ w, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, const float* __restrict__ dx_in,
-                                                     int64_t rows, int dim, int rows_per_cta, float* __restrict__ dx_out,
-                                                     uint16_t* __restrict__ dx_bf16, float* __restrict__ dw) {
-  extern __shared__ float s_dw[];  // 8 warps x dim
+__global__ void __launch_bounds__(128, kDyBf16 ? 5 : 4) ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
+                                                        const float* __restrict__ w, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const float* __restrict__ dx_in,
+                                                        int64_t rows, int dim, int rows_per_cta, float* __restrict__ dx_out,
+                                                        uint16_t* __restrict__ dx_bf16, float* __restrict__ dw) {
+  extern __shared__ float s_dw[];  // 4 warps x dim
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D4 = dim >> 2;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -80,43 +98,51 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* wr = reinterpret_cast<const float4*>(w);
-  for (int64_t row = r0 + warp; row < r1; row += 8) {
+  for (int64_t row = r0 + warp; row < r1; row += 4) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
-    float4 xh[NV], g[NV];
+    float4 xv[NV];
+    DyVec<kDyBf16> dvr[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int i = lane + j * 32;
       if (i < D4) {
-        const float4 xv = xr[i];
-        float4 d;
-        if (kDyBf16) {
-          const uint2 raw = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy_) + row * dim)[i];
-          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-          const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-          d = make_float4(a.x, a.y, b.x, b.y);
-        } else {
-          d = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * dim)[i];
-        }
-        const float4 wv = __ldg(wr + i);
-        xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        acc[j].x += d.x * xh[j].x; acc[j].y += d.y * xh[j].y; acc[j].z += d.z * xh[j].z; acc[j].w += d.w * xh[j].w;
-        g[j] = make_float4(d.x * wv.x, d.y * wv.y, d.z * wv.z, d.w * wv.w);
-        s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
-        s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+        xv[j] = xr[i];
+        dvr[j].load(dy_, row * D4 + i);
       }
     }
-    const float m1 = warp_sum(s1) / dim, m2 = warp_sum(s2) / dim;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int i = lane + j * 32;
       if (i < D4) {
+        const float4 wv = __ldg(wr + i);
+        const float4 d = dvr[j].get();
+        const float hx = (xv[j].x - mu) * rs, hy = (xv[j].y - mu) * rs, hz = (xv[j].z - mu) * rs, hw = (xv[j].w - mu) * rs;
+        acc[j].x += d.x * hx; acc[j].y += d.y * hy; acc[j].z += d.z * hz; acc[j].w += d.w * hw;
+        const float gx = d.x * wv.x, gy = d.y * wv.y, gz = d.z * wv.z, gw = d.w * wv.w;
+        s1 += (gx + gy) + (gz + gw);
+        s2 += (gx * hx + gy * hy) + (gz * hz + gw * hw);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // both reductions in one shuffle chain
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / dim, m2 = s2 / dim;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + j * 32;
+      if (i < D4) {
+        const float4 wv = __ldg(wr + i);
+        const float4 d = dvr[j].get();
+        const float hx = (xv[j].x - mu) * rs, hy = (xv[j].y - mu) * rs, hz = (xv[j].z - mu) * rs, hw = (xv[j].w - mu) * rs;
         float4 o;
-        o.x = rs * (g[j].x - m1 - xh[j].x * m2);
-        o.y = rs * (g[j].y - m1 - xh[j].y * m2);
-        o.z = rs * (g[j].z - m1 - xh[j].z * m2);
-        o.w = rs * (g[j].w - m1 - xh[j].w * m2);
+        o.x = rs * (d.x * wv.x - m1 - hx * m2);
+        o.y = rs * (d.y * wv.y - m1 - hy * m2);
+        o.z = rs * (d.z * wv.z - m1 - hz * m2);
+        o.w = rs * (d.w * wv.w - m1 - hw * m2);
         if (dx_in) {
           const float4 r = reinterpret_cast<const float4*>(dx_in + row * dim)[i];
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -141,7 +167,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   for (int c = threadIdx.x; c < dim; c += blockDim.x) {
     float t = 0.f;
 #pragma unroll
-    for (int wi = 0; wi < 8; ++wi) t += s_dw[wi * dim + c];
+    for (int wi = 0; wi < 4; ++wi) t += s_dw[wi * dim + c];
     atomicAdd(dw + c, t);
   }
 }
@@ -169,18 +195,18 @@ extern "C" int egom2p_layernorm_bwd(const uint16_t* dy_bf16, const float* dy_f32
   EGO_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_bwd: exactly one of dy_bf16 / dy_f32");
   EGO_REQUIRE(x && weight && mean && rstd && dx_out && rows > 0, "layernorm_bwd: null argument");
   EGO_REQUIRE(dim % 4 == 0 && dim > 0 && dim <= kLnMaxVec * 128, "layernorm_bwd: dim %d unsupported", dim);
-  const int rows_per_cta = 32;
+  const int rows_per_cta = 16;
   const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
-  const size_t smem = (size_t)8 * dim * sizeof(float);
+  const size_t smem = (size_t)4 * dim * sizeof(float);
   const int nv = (dim / 4 + 31) / 32;
 #define EGO_LN_BWD(NV)                                                                                                  \
   do {                                                                                                                  \
     if (dy_bf16) {                                                                                                      \
       if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<true, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      ln_bwd_kernel<true, NV><<<grid, 256, smem, (cudaStream_t)stream>>>(dy_bf16, x, weight, mean, rstd, dx_in, rows, dim, rows_per_cta, dx_out, dx_bf16, d_weight); \
+      ln_bwd_kernel<true, NV><<<grid, 128, smem, (cudaStream_t)stream>>>(dy_bf16, x, weight, mean, rstd, dx_in, rows, dim, rows_per_cta, dx_out, dx_bf16, d_weight); \
     } else {                                                                                                            \
       if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<false, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      ln_bwd_kernel<false, NV><<<grid, 256, smem, (cudaStream_t)stream>>>(dy_f32, x, weight, mean, rstd, dx_in, rows, dim, rows_per_cta, dx_out, dx_bf16, d_weight); \
+      ln_bwd_kernel<false, NV><<<grid, 128, smem, (cudaStream_t)stream>>>(dy_f32, x, weight, mean, rstd, dx_in, rows, dim, rows_per_cta, dx_out, dx_bf16, d_weight); \
     }                                                                                                                   \
   } while (0)
   if (nv <= 2) EGO_LN_BWD(2); else if (nv <= 3) EGO_LN_BWD(3); else if (nv <= 4) EGO_LN_BWD(4); else if (nv <= 6) EGO_LN_BWD(6);

@@ -111,7 +111,15 @@ class DecoderBlock(nn.Module):
 # =============================================================================================== kernels glue
 class _Geom:
     """Shapes + key-range tables of one forward (device tensors, no host syncs)."""
-    __slots__ = ("B", "N", "M", "H", "D", "enc_lo", "enc_hi", "dec_lo", "dec_hi", "x_lo", "x_hi", "eps")
+    __slots__ = ("B", "N", "M", "H", "D", "enc_lo", "enc_hi", "dec_lo", "dec_hi", "x_lo", "x_hi", "eps", "m_enc", "m_dec", "m_x")
+
+    def build_meta(self, dev):
+        """Range metadata per attention kind, once per forward (shared by all layers, heads, fwd and bwd)."""
+        if self.N > 0:
+            self.m_enc = ops.attn_ranges(self.B, self.N, self.N, self.enc_lo, self.enc_hi, device=dev)
+        if self.M > 0:
+            self.m_dec = ops.attn_ranges(self.B, self.M, self.M, self.dec_lo, self.dec_hi, device=dev)
+            self.m_x = ops.attn_ranges(self.B, self.M, self.N, self.x_lo, self.x_hi, device=dev)
 
 
 def _zeros(n, dev):
@@ -140,23 +148,23 @@ def _mlp_bwd(dx2, x1, n2w, w13, w2, saved):
     return dx1, dx1b, dn2w, dw13, dw2
 
 
-def _self_attn_fwd(x, n1w, wqkv, wproj, B, L, H, lo, hi, eps):
+def _self_attn_fwd(x, n1w, wqkv, wproj, B, L, H, meta, eps):
     D = x.shape[-1]
     h1, _, mean1, rstd1 = ops.layernorm_fwd(x, n1w, eps)
     qkv = ops.linear_fwd(h1, wqkv)
-    o, lse = ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, L, L, lo, hi)
+    o, lse = ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, L, L, meta=meta)
     x1 = ops.linear_fwd(o, wproj, addend=x, out_dtype=f32)
     return x1, (mean1, rstd1, h1, qkv, o, lse)
 
 
-def _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, saved, B, L, H, lo, hi):
+def _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, saved, B, L, H, meta):
     mean1, rstd1, h1, qkv, o, lse = saved
     D = x.shape[-1]
     dwproj = ops.linear_wgrad(dx1b, o)
     do = ops.linear_dgrad(dx1b, wproj)
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, B, H, L, L, dqkv[:, :D], dqkv[:, D:2 * D],
-                 dqkv[:, 2 * D:], lo, hi)
+                 dqkv[:, 2 * D:], meta=meta)
     dwqkv = ops.linear_wgrad(dqkv, h1)
     dh1 = ops.linear_dgrad(dqkv, wqkv)
     dn1w = _zeros(n1w.numel(), x.device)
@@ -170,7 +178,7 @@ class _EncoderBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, fc3_w, wb, geom):
         wqkv, wproj, w13, w2 = wb
-        x1, sa = _self_attn_fwd(x, n1w, wqkv, wproj, geom.B, geom.N, geom.H, geom.enc_lo, geom.enc_hi, geom.eps)
+        x1, sa = _self_attn_fwd(x, n1w, wqkv, wproj, geom.B, geom.N, geom.H, geom.m_enc, geom.eps)
         x2, sm = _mlp_fwd(x1, n2w, w13, w2, geom.eps)
         ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
         ctx.save_for_backward(x, n1w, n2w, x1, *sa, *sm)
@@ -184,7 +192,7 @@ class _EncoderBlockFn(torch.autograd.Function):
         g = ctx.geom
         dx2 = dx2.contiguous()
         dx1, dx1b, dn2w, dw13, dw2 = _mlp_bwd(dx2, x1, n2w, w13, w2, sm)
-        dx, dn1w, dwqkv, dwproj = _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, sa, g.B, g.N, g.H, g.enc_lo, g.enc_hi)
+        dx, dn1w, dwqkv, dwproj = _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, sa, g.B, g.N, g.H, g.m_enc)
         F, Fp = ctx.F, dw13.shape[0] // 2
         return dx, dn1w, dwqkv, dwproj, dn2w, dw13[:F], dw2[:, :F], dw13[Fp:Fp + F], None, None
 
@@ -197,12 +205,12 @@ class _DecoderBlockFn(torch.autograd.Function):
         wqkv, wsproj, wq, wkv, wxproj, w13, w2 = wb
         g = geom
         D = y.shape[-1]
-        y1, sa = _self_attn_fwd(y, n1w, wqkv, wsproj, g.B, g.M, g.H, g.dec_lo, g.dec_hi, g.eps)
+        y1, sa = _self_attn_fwd(y, n1w, wqkv, wsproj, g.B, g.M, g.H, g.m_dec, g.eps)
         hq, _, meanq, rstdq = ops.layernorm_fwd(y1, qnw, g.eps)
         q = ops.linear_fwd(hq, wq)
         hc, _, meanc, rstdc = ops.layernorm_fwd(context, cnw, g.eps)
         kv = ops.linear_fwd(hc, wkv)
-        o2, lse2 = ops.attn_fwd(q, kv[:, :D], kv[:, D:], g.B, g.H, g.M, g.N, g.x_lo, g.x_hi)
+        o2, lse2 = ops.attn_fwd(q, kv[:, :D], kv[:, D:], g.B, g.H, g.M, g.N, meta=g.m_x)
         y2 = ops.linear_fwd(o2, wxproj, addend=y1, out_dtype=f32)
         y3, sm = _mlp_fwd(y2, n2w, w13, w2, g.eps)
         ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
@@ -225,7 +233,7 @@ class _DecoderBlockFn(torch.autograd.Function):
         do2 = ops.linear_dgrad(dy2b, wxproj)
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
-        ops.attn_bwd(q, kv[:, :D], kv[:, D:], o2, do2, lse2, g.B, g.H, g.M, g.N, dq, dkv[:, :D], dkv[:, D:], g.x_lo, g.x_hi)
+        ops.attn_bwd(q, kv[:, :D], kv[:, D:], o2, do2, lse2, g.B, g.H, g.M, g.N, dq, dkv[:, :D], dkv[:, D:], meta=g.m_x)
         dwq = ops.linear_wgrad(dq, hq)
         dhq = ops.linear_dgrad(dq, wq)
         dwkv = ops.linear_wgrad(dkv, hc)
@@ -233,7 +241,7 @@ class _DecoderBlockFn(torch.autograd.Function):
         dqnw, dcnw = _zeros(D, dev), _zeros(D, dev)
         dy1, dy1b = ops.layernorm_bwd(dhq, y1, qnw, meanq, rstdq, dx_in=dy2, d_weight=dqnw, want_bf16=True)
         dctx, _ = ops.layernorm_bwd(dhc, context, cnw, meanc, rstdc, d_weight=dcnw)
-        dy, dn1w, dwqkv, dwsproj = _self_attn_bwd(dy1, dy1b, y, n1w, wqkv, wsproj, sa, g.B, g.M, g.H, g.dec_lo, g.dec_hi)
+        dy, dn1w, dwqkv, dwsproj = _self_attn_bwd(dy1, dy1b, y, n1w, wqkv, wsproj, sa, g.B, g.M, g.H, g.m_dec)
         F, Fp = ctx.F, dw13.shape[0] // 2
         return (dy, dctx, dn1w, dwqkv, dwsproj, dqnw, dcnw, dwq, dwkv, dwxproj, dn2w, dw13[:F], dw2[:, :F], dw13[Fp:Fp + F],
                 None, None)
@@ -542,6 +550,7 @@ class EgoM2P(nn.Module):
             return x
         g = self._geom(B, N, 0)
         g.enc_lo, g.enc_hi = self._prefix_ranges(encoder_mask, B, N, N, x.device)
+        g.build_meta(x.device)
         h = x.reshape(B * N, D).float().contiguous()
         for i, blk in enumerate(self.encoder):
             h = _EncoderBlockFn.apply(h, blk.norm1.weight, blk.attn.qkv.weight, blk.attn.proj.weight, blk.norm2.weight,
@@ -554,6 +563,9 @@ class EgoM2P(nn.Module):
         g = self._geom(B, N, M)
         g.x_lo, g.x_hi = self._prefix_ranges(encoder_mask, B, M, N, y.device) if N > 0 else (None, None)
         g.dec_lo, g.dec_hi = self._prefix_ranges(decoder_attention_mask, B, M, M, y.device)
+        g.N = 0  # no encoder self-attention on this path
+        g.build_meta(y.device)
+        g.N = N
         h = y.reshape(B * M, D).float().contiguous()
         c = context.reshape(B * N, D).float().contiguous() if N > 0 else torch.zeros(0, D, dtype=f32, device=y.device)
         if N == 0:
@@ -580,6 +592,7 @@ class EgoM2P(nn.Module):
         g = _Geom()
         g.B, g.N, g.M, g.H, g.D, g.eps = B, N, M, self.num_heads, self.dim, self.eps
         g.enc_lo = g.enc_hi = g.dec_lo = g.dec_hi = g.x_lo = g.x_hi = None
+        g.m_enc = g.m_dec = g.m_x = None
         return g
 
     # ------------------------------------------------------------------ the training step (reference :683-734)
@@ -628,6 +641,7 @@ class EgoM2P(nn.Module):
         g.x_lo = torch.zeros(B, M, dtype=torch.int32, device=dev)
         g.x_hi = nv[:, None].expand(B, M).contiguous()
         g.dec_lo, g.dec_hi = dp.key_lo, dp.key_hi
+        g.build_meta(dev)
 
         # ---- fused embed / gather
         elens, evocabs, eids, epos = self._tables("enc", enc_mods, mod_dict, B, dev)

@@ -272,28 +272,41 @@ def lse_stride(Mq: int) -> int:
     return (Mq + 63) // 64 * 64
 
 
-def attn_fwd(q, k, v, B, H, Mq, Nk, key_lo=None, key_hi=None, scale=None, want_lse=True):
-    """q (B*Mq, >=H*64) / k, v (B*Nk, ...) bf16 2-D views with unit inner stride. Returns (o (B*Mq, H*64) bf16, lse)."""
+def attn_ranges(B, Mq, Nk, key_lo=None, key_hi=None, scale=None, device=None):
+    """Range metadata of one (plan, attention kind), built once per forward and shared by all layers / heads."""
     lib = _lib.load()
     scale = (64 ** -0.5) if scale is None else scale
+    device = device if device is not None else key_lo.device
+    meta = torch.empty(lib.egom2p_attn_ranges_bytes(B, Mq), dtype=torch.uint8, device=device)
+    _lib.check(lib.egom2p_attn_ranges(_p(key_lo), _p(key_hi), B, Mq, Nk, scale, _p(meta), _s()), "attn_ranges")
+    return meta
+
+
+def attn_fwd(q, k, v, B, H, Mq, Nk, key_lo=None, key_hi=None, scale=None, want_lse=True, meta=None):
+    """q (B*Mq, >=H*64) / k, v (B*Nk, ...) bf16 2-D views with unit inner stride. Returns (o (B*Mq, H*64) bf16, lse)."""
+    lib = _lib.load()
+    if meta is None:
+        meta = attn_ranges(B, Mq, Nk, key_lo, key_hi, scale, device=q.device)
     o = torch.empty(B * Mq, H * 64, dtype=bf16, device=q.device)
     lse = torch.empty(B, H, lse_stride(Mq), dtype=f32, device=q.device) if want_lse else None
     with _timed("attn_fwd", 4.0 * B * H * Mq * Nk * 64, "flop"):
         _lib.check(lib.egom2p_attn_fwd(_p(q), _p(k) if Nk > 0 else None, _p(v) if Nk > 0 else None, B, H, Mq, Nk, q.stride(0),
-                                       k.stride(0) if Nk > 0 else 0, v.stride(0) if Nk > 0 else 0, _p(key_lo), _p(key_hi),
-                                       scale, _p(o), o.stride(0), _p(lse), _s()), "attn_fwd")
+                                       k.stride(0) if Nk > 0 else 0, v.stride(0) if Nk > 0 else 0, _p(meta), _p(o),
+                                       o.stride(0), _p(lse), _s()), "attn_fwd")
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, B, H, Mq, Nk, dq, dk, dv, key_lo=None, key_hi=None, scale=None):
+def attn_bwd(q, k, v, o, do, lse, B, H, Mq, Nk, dq, dk, dv, key_lo=None, key_hi=None, scale=None, meta=None):
     lib = _lib.load()
     scale = (64 ** -0.5) if scale is None else scale
-    nbytes = lib.egom2p_attn_bwd_scratch_bytes(B, H, Mq)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    if meta is None:
+        meta = attn_ranges(B, Mq, Nk, key_lo, key_hi, scale, device=q.device)
+    assert do.stride(0) == o.stride(0)
+    scratch = torch.empty(lib.egom2p_attn_bwd_scratch_bytes(B, H, Mq), dtype=torch.uint8, device=q.device)
     with _timed("attn_bwd", 10.0 * B * H * Mq * Nk * 64, "flop"):
         _lib.check(lib.egom2p_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), B, H, Mq, Nk, q.stride(0), k.stride(0),
-                                       v.stride(0), o.stride(0), _p(key_lo), _p(key_hi), scale, _p(scratch), _p(dq), _p(dk),
-                                       _p(dv), dq.stride(0), dk.stride(0), dv.stride(0), _s()), "attn_bwd")
+                                       v.stride(0), o.stride(0), _p(meta), scale, _p(scratch), _p(dq), _p(dk), _p(dv),
+                                       dq.stride(0), dk.stride(0), dv.stride(0), _s()), "attn_bwd")
 
 
 # ----------------------------------------------------------------------------------------------- elementwise

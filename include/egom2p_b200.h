@@ -125,22 +125,27 @@ int egom2p_ce_dlogits(const uint16_t* Y, const uint16_t* W, const int64_t* targe
  * (2) Attention, head_dim 64, tcgen05/TMEM tiles fed by TMA, online softmax in fp32
  * (egom2p/models/egom2p_utils.py:185-205 self, :222-244 cross). Q rows live at Q + (b*Mq + i)*ldq + h*64 (same for
  * K/V with Nk, ldk/ldv; O with ldo), so packed qkv / kv projections are consumed in place. Each query row attends
- * the contiguous key range [key_lo[b*Mq+i], key_hi[...]) of its sample (NULL: [0, Nk)). An empty range reproduces the
- * reference's masked_fill(-finfo.max) behaviour: uniform attention over all Nk keys. lse is (B, H, S) fp32 with
- * S = egom2p_attn_lse_stride(Mq) (Mq rounded up to 64), in log2 units (max + log2(sum) of scale*log2e*scores); it is
- * saved for the backward pass.
+ * one contiguous key range [key_lo, key_hi) of its sample (NULL: [0, Nk)); that is every mask this path produces
+ * (encoder key padding, decoder cross, decoder per-modality self-attention, causal). An empty range reproduces the
+ * reference's masked_fill(-finfo.max) behaviour: uniform attention over all Nk keys.
  * ------------------------------------------------------------------------------------------------ */
-int egom2p_attn_lse_stride(int32_t Mq);
+int egom2p_attn_lse_stride(int32_t Mq);                 /* S = Mq rounded up to 64 */
+int64_t egom2p_attn_ranges_bytes(int32_t B, int32_t Mq); /* bytes of the range metadata buffer */
+/* Builds the per-row / per-block range metadata once per forward; it is shared by every layer and head and by the
+ * forward and backward kernels. key_lo / key_hi are (B, Mq) int32 or both NULL. meta: 256-byte aligned. */
+int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, int32_t B, int32_t Mq, int32_t Nk, float scale,
+                       void* meta, void* stream);
+/* lse is (B, H, S) fp32 in log2 units (max + log2(sum) of scale*log2e*scores), saved for the backward pass. */
 int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, int32_t B, int32_t H, int32_t Mq, int32_t Nk,
-                    int64_t ldq, int64_t ldk, int64_t ldv, const int32_t* key_lo, const int32_t* key_hi, float scale,
-                    uint16_t* O, int64_t ldo, float* lse, void* stream);
-/* Bytes of device scratch egom2p_attn_bwd needs (row statistics, per-block key ranges). */
+                    int64_t ldq, int64_t ldk, int64_t ldv, const void* meta, uint16_t* O, int64_t ldo, float* lse,
+                    void* stream);
+/* Bytes of device scratch egom2p_attn_bwd needs (per-row delta terms). */
 int64_t egom2p_attn_bwd_scratch_bytes(int32_t B, int32_t H, int32_t Mq);
-/* dQ/dK/dV use the same addressing as Q/K/V with their own row pitches. */
+/* dQ/dK/dV use the same addressing as Q/K/V with their own row pitches; dO shares O's pitch. */
 int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, const uint16_t* O, const uint16_t* dO,
                     const float* lse, int32_t B, int32_t H, int32_t Mq, int32_t Nk, int64_t ldq, int64_t ldk, int64_t ldv,
-                    int64_t ldo, const int32_t* key_lo, const int32_t* key_hi, float scale, void* scratch, uint16_t* dQ,
-                    uint16_t* dK, uint16_t* dV, int64_t lddq, int64_t lddk, int64_t lddv, void* stream);
+                    int64_t ldo, const void* meta, float scale, void* scratch, uint16_t* dQ, uint16_t* dK, uint16_t* dV,
+                    int64_t lddq, int64_t lddk, int64_t lddv, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Elementwise helpers on the path.
