@@ -67,17 +67,34 @@ struct AttnFwdParams {
   float* lse2;  // (B, H, S), log2 domain: m + log2(l)
 };
 
-constexpr int kFwdStages = 4;
+constexpr int kFwdStages = 3;
+constexpr float kRescaleThreshold = 8.f;  // log2 units: O / l are rescaled only when the row max grows by > 2^8
 struct FwdSmem {
   static constexpr int kQ = 0;
   static constexpr int kK = kQ + kT * 128;
   static constexpr int kV = kK + kFwdStages * kBlk * 128;
-  static constexpr int kP = kV + kFwdStages * kBlk * 128;
-  static constexpr int kX = kP + kT * 128;               // exchange slots: [2 parities][2 halves][128 rows] floats
+  static constexpr int kP = kV + kFwdStages * kBlk * 128;  // two P buffers
+  static constexpr int kX = kP + 2 * kT * 128;             // exchange slots: [2 parities][2 halves][128 rows] floats
   static constexpr int kBar = kX + 2 * 2 * kT * 4;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// O accumulates in TMEM across the whole key loop (tcgen05.mma accumulate), so the math warps never wait for a PV
+// product inside the loop; they only touch O when a row maximum grows by more than 2^8 ("lazy rescaling": until then P
+// and the running sum stay relative to the stale maximum, which is exact after the final O / l division).
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -93,10 +110,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + kFwdStages;
   uint64_t* s_full = kv_empty + kFwdStages;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint64_t* s_free = o_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 1);
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_full = s_free + 1;   // [2]
+  uint64_t* pv_done = p_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
   int* s_range = reinterpret_cast<int*>(tmem_slot + 1);  // [0] = lo, [1] = hi
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,9 +126,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(q_full, 1);
     for (int i = 0; i < kFwdStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 32 * kAttnComputeWarps);
-    mbar_init(o_full, 1);
-    mbar_init(s_free, 32 * kAttnComputeWarps);
+    mbar_init(s_free, kAttnComputeWarps);
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], kAttnComputeWarps); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
     s_range[0] = INT_MAX;
     s_range[1] = INT_MIN;
@@ -152,7 +168,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kBlk, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kD, 0, 1);
       const uint32_t tS = tmem_base, tO = tmem_base + 64;
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      const uint32_t aQ = smem_u32(sQ);
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
@@ -161,7 +177,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_bf16_ss(tS, umma_desc_kmajor_sw128(aQ + k * 32), umma_desc_kmajor_sw128(smem_u32(sK) + k * 32), idesc_s, k ? 1u : 0u);
       umma_commit(s_full);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j % kFwdStages;
+        const int st = j % kFwdStages, buf = j & 1;
         if (j + 1 < nblk) {  // S(j+1) as soon as S(j) sits in registers: overlaps the softmax of block j
           const int st1 = (j + 1) % kFwdStages;
           mbar_wait(s_free, j & 1);
@@ -173,13 +189,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_bf16_ss(tS, umma_desc_kmajor_sw128(aQ + k * 32), umma_desc_kmajor_sw128(aK + k * 32), idesc_s, k ? 1u : 0u);
           umma_commit(s_full);
         }
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[buf], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * kBlk * 128);
+        const uint32_t aV = smem_u32(sV + st * kBlk * 128), aP = smem_u32(sP + buf * kT * 128);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tO, umma_desc_kmajor_sw128(aP + k * 32), umma_desc_mnmajor_sw128(aV + k * 2048, 8192), idesc_pv, k ? 1u : 0u);
-        umma_commit(o_full);
+          umma_bf16_ss(tO, umma_desc_kmajor_sw128(aP + k * 32), umma_desc_mnmajor_sw128(aV + k * 2048, 8192), idesc_pv,
+                       (j | k) ? 1u : 0u);
+        umma_commit(&pv_done[buf]);
         umma_commit(&kv_empty[st]);
       }
     }
@@ -187,11 +204,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---------------------------------------------------------------- softmax warps: thread == (query row, column half)
     const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;
     const uint32_t t_o = tmem_base + ((uint32_t)(quarter * 32) << 16) + 64 + half * 32;
-    float m = -INFINITY, l = 0.f;
-    float o[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) o[c] = 0.f;
+    float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < nblk; ++j) {
+      const int buf = j & 1;
       const int kv0 = lo_cta + j * kBlk + half * 32;  // first key of this thread's 32 columns
       mbar_wait(s_full, j & 1);
       tc_fence_after();
@@ -199,7 +214,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(t_s, v);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
       float sc = rscale;
       if (!(rscale != 0.f && kv0 >= lo && kv0 + 32 <= hi)) {  // block touches the range boundary (or uniform row)
         sc = rscale != 0.f ? rscale : 1.f;
@@ -222,11 +238,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       xs[half * kT + trow] = bm;
       pair_sync(quarter);
       bm = fmaxf(bm, xs[(half ^ 1) * kT + trow]);
-      const float m_new = fmaxf(m, bm);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2(m - m_use);
-      const float nm = -m_use;
+      // lazy rescale: both half-warps of a row see the same bm / m_used, so they take the same decision
+      const bool need = bm > m_used + kRescaleThreshold;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2(m_used - bm) : 1.f;
+        if (need) { m_used = bm; l *= alpha; }
+        if (j > 0) {
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // PV(j-1) has landed: O is stable
+          tc_fence_after();
+          uint32_t ov[32];
+          tmem_ld32(t_o, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+          tmem_st32(t_o, ov);
+          tmem_st_wait();
+          tc_fence_before();
+        }
+      }
+      const float nm = (m_used == -INFINITY) ? 0.f : -m_used;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      if (j >= 2) mbar_wait(&pv_done[buf], ((j - 2) >> 1) & 1);  // PV(j-2) no longer reads this P buffer
+      uint8_t* pb = sP + buf * kT * 128;
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float e[8];
@@ -235,21 +268,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
         uint4 pk;
         pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
-        *reinterpret_cast<uint4*>(sP + swz_off(trow, half * 4 + c8)) = pk;
+        *reinterpret_cast<uint4*>(pb + swz_off(trow, half * 4 + c8)) = pk;
       }
-      l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
-      m = m_new;
+      l += (sum0 + sum1) + (sum2 + sum3);
       fence_async_smem();
-      mbar_arrive(p_full);
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-      tmem_ld32(t_o, v);
-      tmem_ld_wait();
-      tc_fence_before();
-#pragma unroll
-      for (int c = 0; c < 32; ++c) o[c] = o[c] * alpha + __uint_as_float(v[c]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[buf]);
     }
-    // total row sum = both halves
+    // epilogue: O / l
+    uint32_t ov[32];
+    if (nblk > 0) {
+      mbar_wait(&pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
+      tc_fence_after();
+      tmem_ld32(t_o, ov);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) ov[c] = 0u;
+    }
     float* xs = sX + (nblk & 1) * 2 * kT;
     xs[half * kT + trow] = l;
     pair_sync(quarter);
@@ -260,13 +296,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         uint4 pk;
-        pk.x = pack_bf16(o[c8 * 8 + 0] * inv, o[c8 * 8 + 1] * inv);
-        pk.y = pack_bf16(o[c8 * 8 + 2] * inv, o[c8 * 8 + 3] * inv);
-        pk.z = pack_bf16(o[c8 * 8 + 4] * inv, o[c8 * 8 + 5] * inv);
-        pk.w = pack_bf16(o[c8 * 8 + 6] * inv, o[c8 * 8 + 7] * inv);
+        pk.x = pack_bf16(__uint_as_float(ov[c8 * 8 + 0]) * inv, __uint_as_float(ov[c8 * 8 + 1]) * inv);
+        pk.y = pack_bf16(__uint_as_float(ov[c8 * 8 + 2]) * inv, __uint_as_float(ov[c8 * 8 + 3]) * inv);
+        pk.z = pack_bf16(__uint_as_float(ov[c8 * 8 + 4]) * inv, __uint_as_float(ov[c8 * 8 + 5]) * inv);
+        pk.w = pack_bf16(__uint_as_float(ov[c8 * 8 + 6]) * inv, __uint_as_float(ov[c8 * 8 + 7]) * inv);
         reinterpret_cast<uint4*>(orow)[c8] = pk;
       }
-      if (p.lse2 && half == 0) p.lse2[((int64_t)b * p.H + h) * p.S + row] = lt > 0.f ? m + log2f(lt) : INFINITY;
+      if (p.lse2 && half == 0) p.lse2[((int64_t)b * p.H + h) * p.S + row] = lt > 0.f ? m_used + log2f(lt) : INFINITY;
     }
   }
   tc_fence_before();

@@ -56,8 +56,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int i = 0; i < kDqStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 32 * kAttnComputeWarps);
-    mbar_init(ds_full, 32 * kAttnComputeWarps);
+    mbar_init(sdp_free, kAttnComputeWarps);
+    mbar_init(ds_full, kAttnComputeWarps);
     mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);
     fence_mbar_init();
@@ -171,7 +171,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_ld32(t_lane + 64, d);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(sdp_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);
       float sc = rscale;
       if (!(rscale != 0.f && kv0 >= lo && kv0 + 32 <= hi)) {
         sc = rscale != 0.f ? rscale : 1.f;
@@ -195,7 +196,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         *reinterpret_cast<uint4*>(sDS + swz_off(trow, half * 4 + c8)) = pk;
       }
       fence_async_smem();
-      mbar_arrive(ds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
     }
     uint32_t v[32];
     if (nblk > 0) {
@@ -277,8 +279,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(kv_full, 1);
     for (int i = 0; i < kDkvStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 32 * kAttnComputeWarps);
-    mbar_init(pds_full, 32 * kAttnComputeWarps);
+    mbar_init(sdp_free, kAttnComputeWarps);
+    mbar_init(pds_full, kAttnComputeWarps);
     mbar_init(pds_empty, 1);
     mbar_init(dkv_full, 1);
     fence_mbar_init();
@@ -393,7 +395,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(t_lane + 64, d);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(sdp_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);
       if (idx > 0) mbar_wait(pds_empty, (idx - 1) & 1);
       if (inside) {
         // every (key, query) pair of this block is unmasked and every row uses the plain scale
@@ -436,7 +439,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       fence_async_smem();
-      mbar_arrive(pds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
     }
     if (n > 0) {
       mbar_wait(dkv_full, 0);
