@@ -151,31 +151,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nblk = hi_cta > lo_cta ? (hi_cta - lo_cta + kBlk - 1) / kBlk : 0;
 
   if (warp == kTmaWarp) {
-    if (lane == 0 && nblk > 0) {
-      mbar_expect_tx(q_full, kT * 128);
-      tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
+    // warp-uniform control flow (operands stay in uniform registers); one elected lane issues the copies
+    if (nblk > 0) {
+      if (elect_one()) {
+        mbar_expect_tx(q_full, kT * 128);
+        tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
+      }
+      __syncwarp();
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kFwdStages;
         mbar_wait(&kv_empty[st], ((j / kFwdStages) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * kBlk * 128);
         const int krow = b * p.Nk + lo_cta + j * kBlk;
-        tma_load_2d(sK + st * kBlk * 128, &tmK, &kv_full[st], h * kD, krow);
-        tma_load_2d(sV + st * kBlk * 128, &tmV, &kv_full[st], h * kD, krow);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[st], 2 * kBlk * 128);
+          tma_load_2d(sK + st * kBlk * 128, &tmK, &kv_full[st], h * kD, krow);
+          tma_load_2d(sV + st * kBlk * 128, &tmV, &kv_full[st], h * kD, krow);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0 && nblk > 0) {
+    if (nblk > 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kBlk, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kD, 0, 1);
       const uint32_t tS = tmem_base, tO = tmem_base + 64;
-      const uint32_t aQ = smem_u32(sQ);
+      const uint64_t dQ0 = umma_desc_kmajor_sw128(smem_u32(sQ));
+      auto issue_s = [&](int st) {  // S = Q K^T, 4 k-steps of 16
+        const uint64_t dK0 = umma_desc_kmajor_sw128(smem_u32(sK + st * kBlk * 128));
+        if (elect_one()) {
+          umma_bf16_ss(tS, dQ0, dK0, idesc_s, 0u);
+#pragma unroll
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, 1u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+      };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16_ss(tS, umma_desc_kmajor_sw128(aQ + k * 32), umma_desc_kmajor_sw128(smem_u32(sK) + k * 32), idesc_s, k ? 1u : 0u);
-      umma_commit(s_full);
+      issue_s(0);
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kFwdStages, buf = j & 1;
         if (j + 1 < nblk) {  // S(j+1) as soon as S(j) sits in registers: overlaps the softmax of block j
@@ -183,21 +197,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_wait(s_free, j & 1);
           mbar_wait(&kv_full[st1], ((j + 1) / kFwdStages) & 1);
           tc_fence_after();
-          const uint32_t aK = smem_u32(sK + st1 * kBlk * 128);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tS, umma_desc_kmajor_sw128(aQ + k * 32), umma_desc_kmajor_sw128(aK + k * 32), idesc_s, k ? 1u : 0u);
-          umma_commit(s_full);
+          issue_s(st1);
         }
         mbar_wait(&p_full[buf], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * kBlk * 128), aP = smem_u32(sP + buf * kT * 128);
+        const uint64_t dP0 = umma_desc_kmajor_sw128(smem_u32(sP + buf * kT * 128));
+        const uint64_t dV0 = umma_desc_mnmajor_sw128(smem_u32(sV + st * kBlk * 128), 8192);
+        if (elect_one()) {
+          umma_bf16_ss(tO, dP0, dV0, idesc_pv, j ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tO, umma_desc_kmajor_sw128(aP + k * 32), umma_desc_mnmajor_sw128(aV + k * 2048, 8192), idesc_pv,
-                       (j | k) ? 1u : 0u);
-        umma_commit(&pv_done[buf]);
-        umma_commit(&kv_empty[st]);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tO, dP0 + 2 * k, dV0 + 128 * k, idesc_pv, 1u);
+          umma_commit(&pv_done[buf]);
+          umma_commit(&kv_empty[st]);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -82,34 +82,45 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int nblk = hi_cta > lo_cta ? (hi_cta - lo_cta + kBlk - 1) / kBlk : 0;
 
   if (warp == kTmaWarp) {
-    if (lane == 0 && nblk > 0) {
-      mbar_expect_tx(q_full, 2 * kT * 128);
-      tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
-      tma_load_2d(sDO, &tmDO, q_full, h * kD, b * p.Mq + q0);
+    if (nblk > 0) {
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kT * 128);
+        tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
+        tma_load_2d(sDO, &tmDO, q_full, h * kD, b * p.Mq + q0);
+      }
+      __syncwarp();
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kDqStages;
         mbar_wait(&kv_empty[st], ((j / kDqStages) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * kBlk * 128);
         const int krow = b * p.Nk + lo_cta + j * kBlk;
-        tma_load_2d(sK + st * kBlk * 128, &tmK, &kv_full[st], h * kD, krow);
-        tma_load_2d(sV + st * kBlk * 128, &tmV, &kv_full[st], h * kD, krow);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[st], 2 * kBlk * 128);
+          tma_load_2d(sK + st * kBlk * 128, &tmK, &kv_full[st], h * kD, krow);
+          tma_load_2d(sV + st * kBlk * 128, &tmV, &kv_full[st], h * kD, krow);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0 && nblk > 0) {
+    if (nblk > 0) {
       constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBlk, 0, 0);
       constexpr uint32_t idesc_kmn = umma_idesc_bf16(128, kD, 0, 1);
       const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128;
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aDS = smem_u32(sDS);
+      const uint64_t dQ0 = umma_desc_kmajor_sw128(smem_u32(sQ)), dDO0 = umma_desc_kmajor_sw128(smem_u32(sDO));
+      const uint64_t dDS0 = umma_desc_kmajor_sw128(smem_u32(sDS));
       auto issue_sdp = [&](int st) {
-        const uint32_t aK = smem_u32(sK + st * kBlk * 128), aV = smem_u32(sV + st * kBlk * 128);
+        const uint64_t dK0 = umma_desc_kmajor_sw128(smem_u32(sK + st * kBlk * 128));
+        const uint64_t dV0 = umma_desc_kmajor_sw128(smem_u32(sV + st * kBlk * 128));
+        if (elect_one()) {
+          umma_bf16_ss(tS, dQ0, dK0, idesc_kk, 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tS, umma_desc_kmajor_sw128(aQ + k * 32), umma_desc_kmajor_sw128(aK + k * 32), idesc_kk, k ? 1u : 0u);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_kk, 1u);
+          umma_bf16_ss(tDP, dDO0, dV0, idesc_kk, 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tDP, umma_desc_kmajor_sw128(aDO + k * 32), umma_desc_kmajor_sw128(aV + k * 32), idesc_kk, k ? 1u : 0u);
-        umma_commit(sdp_full);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tDP, dDO0 + 2 * k, dV0 + 2 * k, idesc_kk, 1u);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
@@ -126,15 +137,17 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         mbar_wait(ds_full, j & 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sK + st * kBlk * 128);
+        const uint64_t dKm0 = umma_desc_mnmajor_sw128(smem_u32(sK + st * kBlk * 128), 8192);
+        if (elect_one()) {
+          umma_bf16_ss(tDQ, dDS0, dKm0, idesc_kmn, j ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tDQ, umma_desc_kmajor_sw128(aDS + k * 32), umma_desc_mnmajor_sw128(aK + k * 2048, 8192), idesc_kmn,
-                       (j | k) ? 1u : 0u);
-        umma_commit(ds_empty);
-        umma_commit(&kv_empty[st]);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tDQ, dDS0 + 2 * k, dKm0 + 128 * k, idesc_kmn, 1u);
+          umma_commit(ds_empty);
+          umma_commit(&kv_empty[st]);
+          if (j == nblk - 1) umma_commit(dq_full);
+        }
+        __syncwarp();
       }
-      umma_commit(dq_full);
     }
   } else {
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;
@@ -310,41 +323,52 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n = *s_n;
 
   if (warp == kTmaWarp) {
-    if (lane == 0 && n > 0) {
-      mbar_expect_tx(kv_full, 2 * kT * 128);
-      tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
-      tma_load_2d(sV, &tmV, kv_full, h * kD, b * p.Nk + kv0);
+    if (n > 0) {
+      if (elect_one()) {
+        mbar_expect_tx(kv_full, 2 * kT * 128);
+        tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
+        tma_load_2d(sV, &tmV, kv_full, h * kD, b * p.Nk + kv0);
+      }
+      __syncwarp();
       for (int idx = 0; idx < n; ++idx) {
         const int st = idx % kDkvStages;
         const int r0 = (int)(s_list[idx] & 0x7fff) * kBlk;
         mbar_wait(&q_empty[st], ((idx / kDkvStages) & 1) ^ 1);
-        mbar_expect_tx(&q_full[st], 2 * kBlk * 128 + kMetaBytes);
-        tma_load_2d(sQ + st * kBlk * 128, &tmQ, &q_full[st], h * kD, b * p.Mq + r0);
-        tma_load_2d(sDO + st * kBlk * 128, &tmDO, &q_full[st], h * kD, b * p.Mq + r0);
         uint8_t* meta = sMeta + st * kMetaBytes;
         const int64_t hoff = ((int64_t)b * p.H + h) * p.S + r0, roff = (int64_t)b * p.S + r0;
-        bulk_load(meta + 0 * 256, p.lse2 + hoff, 256, &q_full[st]);
-        bulk_load(meta + 1 * 256, p.ndelta + hoff, 256, &q_full[st]);
-        bulk_load(meta + 2 * 256, p.meta.row_lo + roff, 256, &q_full[st]);
-        bulk_load(meta + 3 * 256, p.meta.row_hi + roff, 256, &q_full[st]);
-        bulk_load(meta + 4 * 256, p.meta.row_scale + roff, 256, &q_full[st]);
+        if (elect_one()) {
+          mbar_expect_tx(&q_full[st], 2 * kBlk * 128 + kMetaBytes);
+          tma_load_2d(sQ + st * kBlk * 128, &tmQ, &q_full[st], h * kD, b * p.Mq + r0);
+          tma_load_2d(sDO + st * kBlk * 128, &tmDO, &q_full[st], h * kD, b * p.Mq + r0);
+          bulk_load(meta + 0 * 256, p.lse2 + hoff, 256, &q_full[st]);
+          bulk_load(meta + 1 * 256, p.ndelta + hoff, 256, &q_full[st]);
+          bulk_load(meta + 2 * 256, p.meta.row_lo + roff, 256, &q_full[st]);
+          bulk_load(meta + 3 * 256, p.meta.row_hi + roff, 256, &q_full[st]);
+          bulk_load(meta + 4 * 256, p.meta.row_scale + roff, 256, &q_full[st]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0 && n > 0) {
+    if (n > 0) {
       constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBlk, 0, 0);
       constexpr uint32_t idesc_kmn = umma_idesc_bf16(128, kD, 0, 1);
       const uint32_t tST = tmem_base, tDPT = tmem_base + 64, tDV = tmem_base + 128, tDK = tmem_base + 192;
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), aDST = smem_u32(sDST);
+      const uint64_t dK0 = umma_desc_kmajor_sw128(smem_u32(sK)), dV0 = umma_desc_kmajor_sw128(smem_u32(sV));
+      const uint64_t dPT0 = umma_desc_kmajor_sw128(smem_u32(sPT)), dDST0 = umma_desc_kmajor_sw128(smem_u32(sDST));
       auto issue_sdp = [&](int st) {
-        const uint32_t aQ = smem_u32(sQ + st * kBlk * 128), aDO = smem_u32(sDO + st * kBlk * 128);
+        const uint64_t dQ0 = umma_desc_kmajor_sw128(smem_u32(sQ + st * kBlk * 128));
+        const uint64_t dDO0 = umma_desc_kmajor_sw128(smem_u32(sDO + st * kBlk * 128));
+        if (elect_one()) {
+          umma_bf16_ss(tST, dK0, dQ0, idesc_kk, 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tST, umma_desc_kmajor_sw128(aK + k * 32), umma_desc_kmajor_sw128(aQ + k * 32), idesc_kk, k ? 1u : 0u);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tST, dK0 + 2 * k, dQ0 + 2 * k, idesc_kk, 1u);
+          umma_bf16_ss(tDPT, dV0, dDO0, idesc_kk, 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tDPT, umma_desc_kmajor_sw128(aV + k * 32), umma_desc_kmajor_sw128(aDO + k * 32), idesc_kk, k ? 1u : 0u);
-        umma_commit(sdp_full);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tDPT, dV0 + 2 * k, dDO0 + 2 * k, idesc_kk, 1u);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
@@ -361,19 +385,21 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         mbar_wait(pds_full, idx & 1);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ + st * kBlk * 128), aDO = smem_u32(sDO + st * kBlk * 128);
+        const uint64_t dQm0 = umma_desc_mnmajor_sw128(smem_u32(sQ + st * kBlk * 128), 8192);
+        const uint64_t dDOm0 = umma_desc_mnmajor_sw128(smem_u32(sDO + st * kBlk * 128), 8192);
+        if (elect_one()) {
+          umma_bf16_ss(tDV, dPT0, dDOm0, idesc_kmn, idx ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tDV, umma_desc_kmajor_sw128(aPT + k * 32), umma_desc_mnmajor_sw128(aDO + k * 2048, 8192), idesc_kmn,
-                       (idx | k) ? 1u : 0u);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tDV, dPT0 + 2 * k, dDOm0 + 128 * k, idesc_kmn, 1u);
+          umma_bf16_ss(tDK, dDST0, dQm0, idesc_kmn, idx ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tDK, umma_desc_kmajor_sw128(aDST + k * 32), umma_desc_mnmajor_sw128(aQ + k * 2048, 8192), idesc_kmn,
-                       (idx | k) ? 1u : 0u);
-        umma_commit(pds_empty);
-        umma_commit(&q_empty[st]);
+          for (int k = 1; k < 4; ++k) umma_bf16_ss(tDK, dDST0 + 2 * k, dQm0 + 128 * k, idesc_kmn, 1u);
+          umma_commit(pds_empty);
+          umma_commit(&q_empty[st]);
+          if (idx == n - 1) umma_commit(dkv_full);
+        }
+        __syncwarp();
       }
-      umma_commit(dkv_full);
     }
   } else {
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;

@@ -99,19 +99,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int tile = item / splits, split = item - tile * splits;
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          const int k0 = kb * BK;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // The whole warp walks the loop (addresses / coordinates stay in uniform registers); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = item / splits, split = item - tile * splits;
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int k0 = kb * BK;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* a = sA + stage * S::kABytes;
+        uint8_t* b = sB + stage * S::kBBytes;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-          uint8_t* a = sA + stage * S::kABytes;
-          uint8_t* b = sB + stage * S::kBBytes;
           if (!A_MN) {
             tma_load_2d(a, &tmA, &full_bar[stage], k0, m0);
           } else {
@@ -124,40 +125,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h) tma_load_2d(b + h * 8192, &tmB, &full_bar[stage], n0 + h * 64, k0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-        const int split = item % splits;
-        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ------------------------------------------------------------------ MMA issuer
+    // Warp-uniform loop; descriptors are built once per stage in uniform registers and advanced by a constant per
+    // k-step, so each tcgen05.mma costs a couple of instructions to issue (the tensor pipe needs one every 128 cycles).
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint64_t kStepA = A_MN ? (2048 >> 4) : (32 >> 4), kStepB = B_MN ? (2048 >> 4) : (32 >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int split = item % splits;
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
+        const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
+        const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
+        const uint64_t da0 = A_MN ? umma_desc_mnmajor_sw128(a_addr, 8192) : umma_desc_kmajor_sw128(a_addr);
+        const uint64_t db0 = B_MN ? umma_desc_mnmajor_sw128(b_addr, 8192) : umma_desc_kmajor_sw128(b_addr);
+        if (elect_one()) {
+          umma_bf16_ss(d_tmem, da0, db0, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_desc_mnmajor_sw128(a_addr + k * 2048, 8192) : umma_desc_kmajor_sw128(a_addr + k * 32);
-            const uint64_t db = B_MN ? umma_desc_mnmajor_sw128(b_addr + k * 2048, 8192) : umma_desc_kmajor_sw128(b_addr + k * 32);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 1; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da0 + k * kStepA, db0 + k * kStepB, idesc, 1u);
           umma_commit(&empty_bar[stage]);
           if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
