@@ -38,6 +38,8 @@ SIGNATURES = {
     "egom2p_layernorm_fwd": [vp, vp, i64, i32, f32, vp, vp, vp, vp, vp],
     "egom2p_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp],
     "egom2p_gemm_bf16": [vp, vp, i32, i32, i32, i64, i64, i32, i32, vp, vp, i64, vp, vp, i64, vp],
+    "egom2p_gemm_swiglu_fwd": [vp, vp, i32, i32, i32, i64, i64, vp, i64, vp, i64, vp],
+    "egom2p_gemm_swiglu_bwd": [vp, vp, vp, i32, i32, i32, i64, i64, i64, vp, i64, vp],
     "egom2p_ce_partials": [vp, vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp],
     "egom2p_ce_finalize": [vp, vp, vp, i32, i32, vp, vp, vp],
     "egom2p_ce_dlogits": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, vp, i64, vp],

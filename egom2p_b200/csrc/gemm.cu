@@ -19,7 +19,7 @@ constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
-enum { EPI_STORE = 0, EPI_CE_PARTIAL = 1, EPI_CE_DLOGITS = 2 };
+enum { EPI_STORE = 0, EPI_CE_PARTIAL = 1, EPI_CE_DLOGITS = 2, EPI_SWIGLU_FWD = 3, EPI_SWIGLU_BWD = 4 };
 
 struct GemmParams {
   int M, N, K;
@@ -33,6 +33,9 @@ struct GemmParams {
   const int64_t* target;
   const float* lse;
   const float* gscale;
+  // SwiGLU epilogues: ab = [a | b] interleaved in groups of 32 columns (bf16), row pitch ld_ab
+  const uint16_t* ab;
+  int64_t ld_ab;
   int v0;
   float* part_max;
   float* part_sum;
@@ -188,7 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int row_tgt = -1;
       float run_max = -INFINITY, run_sum = 0.f, tl = 0.f;
       bool has_tl = false;
-      if (EPI != EPI_STORE && row_ok) {
+      if ((EPI == EPI_CE_PARTIAL || EPI == EPI_CE_DLOGITS) && row_ok) {
         row_tgt = (int)p.target[my_row] - p.v0;
         if (EPI == EPI_CE_DLOGITS) {
           row_lse = p.lse[my_row];
@@ -224,6 +227,107 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           p.part_max[o] = run_max;
           p.part_sum[o] = run_sum;
           if (has_tl) p.tgt_logit[my_row] = tl;
+        }
+      } else if (EPI == EPI_SWIGLU_FWD) {
+        // ---- fc1|fc3 GEMM: accumulator columns come in groups of 64 = 32 x a | 32 x b (interleaved weight rows).
+        // Per 128 columns: store the two pre-activation boxes (bf16, saved for backward) and one box of
+        // g = silu(a) * b (64 columns) -- the operand of the fc2 GEMM (egom2p_utils.py:167-169).
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols / 128; ++c) {
+          uint32_t gp[32];  // 64 packed bf16 gate values
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_addr + c * 128 + hh * 64, v0);
+            tmem_ld32(t_addr + c * 128 + hh * 64 + 32, v1);
+            tmem_ld_wait();
+            const int cbase = n0 + c * 128 + hh * 64;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
+              const float g0 = a0 / (1.f + __expf(-a0)) * __uint_as_float(v1[2 * j]);
+              const float g1 = a1 / (1.f + __expf(-a1)) * __uint_as_float(v1[2 * j + 1]);
+              gp[hh * 16 + j] = pack_bf16(g0, g1);
+            }
+            tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              pk.x = pack_bf16(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
+              pk.y = pack_bf16(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
+              pk.z = pack_bf16(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
+              pk.w = pack_bf16(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
+              *reinterpret_cast<uint4*>(box + box_off(lane, j)) = pk;
+              pk.x = pack_bf16(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
+              pk.y = pack_bf16(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
+              pk.z = pack_bf16(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
+              pk.w = pack_bf16(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
+              *reinterpret_cast<uint4*>(box + box_off(lane, j + 4)) = pk;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M && cbase < p.N) {
+              tma_store_2d(&tmCb, box, cbase, row0);
+              tma_store_commit();
+            }
+          }
+          tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(box + box_off(lane, j)) = make_uint4(gp[4 * j], gp[4 * j + 1], gp[4 * j + 2], gp[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          const int gbase = (n0 + c * 128) >> 1;
+          if (lane == 0 && row0 < p.M && gbase < (p.N >> 1)) {
+            tma_store_2d(&tmCf, box, gbase, row0);   // aux map = g (rows, N/2) bf16
+            tma_store_commit();
+          }
+        }
+      } else if (EPI == EPI_SWIGLU_BWD) {
+        // ---- fc2 dgrad: acc = dg (32 columns per step); with the saved [a | b] group of the same 32 hidden units emit
+        // [da | db] (64 bf16 columns, same interleaved layout): da = dg * b * silu'(a), db = dg * silu(a).
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          const int cbase = n0 + c * 32;           // hidden-unit base of this step
+          uint32_t da[16], db[16];
+          if (row_ok && cbase < p.N) {
+            const uint4* pab = reinterpret_cast<const uint4*>(p.ab + (int64_t)my_row * p.ld_ab + 2 * cbase);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 ra = pab[j], rb = pab[j + 4];
+              const uint32_t aw[4] = {ra.x, ra.y, ra.z, ra.w}, bw[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[u]));
+                const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[u]));
+                const float d0 = __uint_as_float(v[8 * j + 2 * u]), d1 = __uint_as_float(v[8 * j + 2 * u + 1]);
+                const float s0 = 1.f / (1.f + __expf(-fa.x)), s1 = 1.f / (1.f + __expf(-fa.y));
+                da[4 * j + u] = pack_bf16(d0 * fb.x * (s0 * (1.f + fa.x * (1.f - s0))), d1 * fb.y * (s1 * (1.f + fa.y * (1.f - s1))));
+                db[4 * j + u] = pack_bf16(d0 * fa.x * s0, d1 * fa.y * s1);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { da[j] = 0u; db[j] = 0u; }
+          }
+          tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(box + box_off(lane, j)) = make_uint4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
+            *reinterpret_cast<uint4*>(box + box_off(lane, j + 4)) = make_uint4(db[4 * j], db[4 * j + 1], db[4 * j + 2], db[4 * j + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && cbase < p.N) {
+            tma_store_2d(&tmCb, box, 2 * cbase, row0);   // output map = dab (rows, 2N) bf16
+            tma_store_commit();
+          }
         }
       } else if (EPI == EPI_CE_DLOGITS || p.out_bf16) {
         // ---- bf16 output: 64 columns (one 128-byte box row) per step
@@ -354,8 +458,15 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   if (rc) return rc;
   tmCb = tmA;
   tmCf = tmA;
-  if (c_bf16 && (rc = make_tmap_2d(&tmCb, c_bf16, 2, p.M, p.N, ldc, 32, 64))) return rc;
-  if (c_f32 && (rc = make_tmap_2d(&tmCf, c_f32, 4, p.M, p.N, ldc, 32, 32))) return rc;
+  if (EPI == EPI_SWIGLU_BWD) {          // c_bf16 = dab (M, 2N)
+    if ((rc = make_tmap_2d(&tmCb, c_bf16, 2, p.M, 2 * (uint64_t)p.N, ldc, 32, 64))) return rc;
+  } else if (EPI == EPI_SWIGLU_FWD) {   // c_bf16 = ab (M, N); c_f32 slot carries g (M, N/2) bf16 with pitch p.ld_ab
+    if ((rc = make_tmap_2d(&tmCb, c_bf16, 2, p.M, p.N, ldc, 32, 64))) return rc;
+    if ((rc = make_tmap_2d(&tmCf, c_f32, 2, p.M, (uint64_t)p.N / 2, p.ld_ab, 32, 64))) return rc;
+  } else {
+    if (c_bf16 && (rc = make_tmap_2d(&tmCb, c_bf16, 2, p.M, p.N, ldc, 32, 64))) return rc;
+    if (c_f32 && (rc = make_tmap_2d(&tmCf, c_f32, 4, p.M, p.N, ldc, 32, 32))) return rc;
+  }
   p.out_bf16 = c_bf16 != nullptr;
   p.out_f32 = c_f32 != nullptr;
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
@@ -399,7 +510,9 @@ static int dispatch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int6
   const int64_t tiles256 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + 255) / 256);
   const bool use256 = (EPI != EPI_STORE) || (p.N >= 256 && (tiles256 >= 2 * sms || !c_bf16));
 #define EGO_GEMM_CASE(BN_, AM, BMJ) return launch_gemm<BN_, AM, BMJ, EPI>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream)
-  if constexpr (EPI != EPI_STORE) {  // CE epilogues: Y (K-major) x W (K-major)
+  if constexpr (EPI == EPI_SWIGLU_BWD) {  // dg = dY W2 (B consumed MN-major)
+    EGO_GEMM_CASE(256, false, true);
+  } else if constexpr (EPI != EPI_STORE) {  // CE / SwiGLU-forward epilogues: K-major x K-major
     EGO_GEMM_CASE(256, false, false);
   } else if (use256) {
     if (!a_mn && !b_mn) EGO_GEMM_CASE(256, false, false);
@@ -448,6 +561,27 @@ extern "C" int egom2p_ce_dlogits(const uint16_t* Y, const uint16_t* W, const int
   GemmParams p{};
   p.M = R; p.N = Vc; p.K = K; p.target = target; p.lse = lse; p.gscale = gscale; p.v0 = v0;
   return dispatch_gemm<EPI_CE_DLOGITS>(Y, W + (int64_t)v0 * ldw, ldy, ldw, 0, 0, dlogits, nullptr, ldd, p, (cudaStream_t)stream);
+}
+
+extern "C" int egom2p_gemm_swiglu_fwd(const uint16_t* X, const uint16_t* W13, int32_t M, int32_t N2, int32_t K, int64_t ldx,
+                                      int64_t ldw, uint16_t* ab, int64_t ld_ab, uint16_t* g, int64_t ldg, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(X && W13 && ab && g && M > 0 && N2 > 0 && K > 0, "gemm_swiglu_fwd: bad argument");
+  EGO_REQUIRE(N2 % 64 == 0 && ld_ab % 8 == 0 && ldg % 8 == 0, "gemm_swiglu_fwd: 2*hidden must be a multiple of 64 (32-wide a|b groups)");
+  GemmParams p{};
+  p.M = M; p.N = N2; p.K = K; p.ld_ab = ldg;
+  return dispatch_gemm<EPI_SWIGLU_FWD>(X, W13, ldx, ldw, 0, 0, ab, reinterpret_cast<float*>(g), ld_ab, p, (cudaStream_t)stream);
+}
+
+extern "C" int egom2p_gemm_swiglu_bwd(const uint16_t* dY, const uint16_t* W2, const uint16_t* ab, int32_t M, int32_t hidden,
+                                      int32_t K, int64_t ldy, int64_t ldw, int64_t ld_ab, uint16_t* dab, int64_t ld_dab,
+                                      void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(dY && W2 && ab && dab && M > 0 && hidden > 0 && K > 0, "gemm_swiglu_bwd: bad argument");
+  EGO_REQUIRE(hidden % 32 == 0 && ld_ab % 8 == 0 && ld_dab % 8 == 0, "gemm_swiglu_bwd: hidden must be a multiple of 32");
+  GemmParams p{};
+  p.M = M; p.N = hidden; p.K = K; p.ab = ab; p.ld_ab = ld_ab;
+  return dispatch_gemm<EPI_SWIGLU_BWD>(dY, W2, ldy, ldw, 0, 1, dab, nullptr, ld_dab, p, (cudaStream_t)stream);
 }
 
 namespace egom2p {

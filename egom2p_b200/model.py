@@ -126,10 +126,16 @@ def _zeros(n, dev):
     return torch.zeros(n, dtype=f32, device=dev)
 
 
+def _split_w13_grad(dw13, F):
+    """dw13 rows are interleaved [32 x fc1 | 32 x fc3] groups (see EgoM2P._bf16_w13): back to (fc1.grad, fc3.grad)."""
+    Fp, D = dw13.shape[0] // 2, dw13.shape[1]
+    v = dw13.view(Fp // 32, 2, 32, D)
+    return v[:, 0].reshape(Fp, D)[:F], v[:, 1].reshape(Fp, D)[:F]
+
+
 def _mlp_fwd(x1, n2w, w13, w2, eps):
     h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, eps)
-    ab = ops.linear_fwd(h2, w13)
-    g = ops.swiglu_fwd(ab)
+    ab, g = ops.gemm_swiglu_fwd(h2, w13)   # fc1|fc3 GEMM with the SwiGLU gate in its epilogue
     x2 = ops.linear_fwd(g, w2, addend=x1, out_dtype=f32)
     return x2, (mean2, rstd2, h2, ab, g)
 
@@ -139,8 +145,7 @@ def _mlp_bwd(dx2, x1, n2w, w13, w2, saved):
     mean2, rstd2, h2, ab, g = saved
     dx2b = ops.cast_bf16(dx2)
     dw2 = ops.linear_wgrad(dx2b, g)
-    dg = ops.linear_dgrad(dx2b, w2)
-    dab = ops.swiglu_bwd(ab, dg)
+    dab = ops.gemm_swiglu_bwd(dx2b, w2, ab)   # fc2 dgrad with the SwiGLU derivative in its epilogue
     dw13 = ops.linear_wgrad(dab, h2)
     dh2 = ops.linear_dgrad(dab, w13)
     dn2w = _zeros(n2w.numel(), dx2.device)
@@ -193,8 +198,9 @@ class _EncoderBlockFn(torch.autograd.Function):
         dx2 = dx2.contiguous()
         dx1, dx1b, dn2w, dw13, dw2 = _mlp_bwd(dx2, x1, n2w, w13, w2, sm)
         dx, dn1w, dwqkv, dwproj = _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, sa, g.B, g.N, g.H, g.m_enc)
-        F, Fp = ctx.F, dw13.shape[0] // 2
-        return dx, dn1w, dwqkv, dwproj, dn2w, dw13[:F], dw2[:, :F], dw13[Fp:Fp + F], None, None
+        F = ctx.F
+        d1, d3 = _split_w13_grad(dw13, F)
+        return dx, dn1w, dwqkv, dwproj, dn2w, d1, dw2[:, :F], d3, None, None
 
 
 class _DecoderBlockFn(torch.autograd.Function):
@@ -242,9 +248,9 @@ class _DecoderBlockFn(torch.autograd.Function):
         dy1, dy1b = ops.layernorm_bwd(dhq, y1, qnw, meanq, rstdq, dx_in=dy2, d_weight=dqnw, want_bf16=True)
         dctx, _ = ops.layernorm_bwd(dhc, context, cnw, meanc, rstdc, d_weight=dcnw)
         dy, dn1w, dwqkv, dwsproj = _self_attn_bwd(dy1, dy1b, y, n1w, wqkv, wsproj, sa, g.B, g.M, g.H, g.m_dec)
-        F, Fp = ctx.F, dw13.shape[0] // 2
-        return (dy, dctx, dn1w, dwqkv, dwsproj, dqnw, dcnw, dwq, dwkv, dwxproj, dn2w, dw13[:F], dw2[:, :F], dw13[Fp:Fp + F],
-                None, None)
+        F = ctx.F
+        d1, d3 = _split_w13_grad(dw13, F)
+        return (dy, dctx, dn1w, dwqkv, dwsproj, dqnw, dcnw, dwq, dwkv, dwxproj, dn2w, d1, dw2[:, :F], d3, None, None)
 
 
 class _ContextFn(torch.autograd.Function):
@@ -483,7 +489,7 @@ class EgoM2P(nn.Module):
         return no_wd
 
     # ------------------------------------------------------------------ bf16 operand cache (refreshed when a master changes)
-    def _bf16(self, key, *params: torch.Tensor) -> torch.Tensor:
+    def _bf16(self, key, *params: torch.Tensor, pad32: bool = False) -> torch.Tensor:
         ver = tuple((p.data_ptr(), p._version) for p in params)
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == ver:
@@ -491,32 +497,37 @@ class EgoM2P(nn.Module):
         dev = params[0].device
         if len(params) == 1:
             p = params[0]
-            pad = (-p.shape[1]) % 8
+            pad = (-p.shape[1]) % (32 if pad32 else 8)
             if pad == 0:
                 out = hit[1] if hit is not None and hit[1].shape == p.shape else None
                 wb = ops.cast_bf16(p.detach(), out)
             else:  # inner dim padded with zero columns so TMA row pitches stay 16-byte multiples (e.g. hidden 682)
                 wb = hit[1] if hit is not None else torch.zeros(p.shape[0], p.shape[1] + pad, dtype=bf16, device=dev)
                 wb[:, :p.shape[1]].copy_(ops.cast_bf16(p.detach()))
-        else:  # row-wise concatenation (fc1 | fc3 -> one N = 2*hidden GEMM), each part padded to a multiple of 8 rows
-            rp = (params[0].shape[0] + 7) // 8 * 8
-            wb = hit[1] if hit is not None else torch.zeros(rp * len(params), params[0].shape[1], dtype=bf16, device=dev)
+        else:  # fc1 | fc3 -> one N = 2*hidden GEMM operand with rows interleaved in groups of 32 (hidden padded to 32)
+            F, D = params[0].shape
+            Fp = (F + 31) // 32 * 32
+            wb = hit[1] if hit is not None else torch.zeros(2 * Fp, D, dtype=bf16, device=dev)
+            v = wb.view(Fp // 32, 2, 32, D)
             for i, p in enumerate(params):
-                ops.cast_bf16(p.detach(), wb[i * rp:i * rp + p.shape[0]])
+                tmp = ops.cast_bf16(p.detach())
+                if Fp != F:
+                    tmp = torch.cat([tmp, torch.zeros(Fp - F, D, dtype=bf16, device=dev)], 0)
+                v[:, i].copy_(tmp.view(Fp // 32, 32, D))
         self._wcache[key] = (ver, wb)
         return wb
 
     def _enc_weights(self, i: int):
         b = self.encoder[i]
         return (self._bf16(("e", i, "qkv"), b.attn.qkv.weight), self._bf16(("e", i, "proj"), b.attn.proj.weight),
-                self._bf16(("e", i, "w13"), b.mlp.fc1.weight, b.mlp.fc3.weight), self._bf16(("e", i, "w2"), b.mlp.fc2.weight))
+                self._bf16(("e", i, "w13"), b.mlp.fc1.weight, b.mlp.fc3.weight), self._bf16(("e", i, "w2"), b.mlp.fc2.weight, pad32=True))
 
     def _dec_weights(self, i: int):
         b = self.decoder[i]
         return (self._bf16(("d", i, "qkv"), b.self_attn.qkv.weight), self._bf16(("d", i, "sproj"), b.self_attn.proj.weight),
                 self._bf16(("d", i, "q"), b.cross_attn.q.weight), self._bf16(("d", i, "kv"), b.cross_attn.kv.weight),
                 self._bf16(("d", i, "xproj"), b.cross_attn.proj.weight),
-                self._bf16(("d", i, "w13"), b.mlp.fc1.weight, b.mlp.fc3.weight), self._bf16(("d", i, "w2"), b.mlp.fc2.weight))
+                self._bf16(("d", i, "w13"), b.mlp.fc1.weight, b.mlp.fc3.weight), self._bf16(("d", i, "w2"), b.mlp.fc2.weight, pad32=True))
 
     # ------------------------------------------------------------------ sampler-facing pieces (reference :251-283,483-551)
     def cat_encoder_tensors(self, mod_dict):

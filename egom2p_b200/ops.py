@@ -208,6 +208,31 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn=False
     return out
 
 
+def gemm_swiglu_fwd(x: torch.Tensor, w13: torch.Tensor):
+    """ab = x @ w13^T (bf16, interleaved [a | b] groups of 32) and g = silu(a) * b, gate fused into the GEMM epilogue."""
+    lib = _lib.load()
+    R, K = x.shape
+    N2 = w13.shape[0]
+    ab = torch.empty(R, N2, dtype=bf16, device=x.device)
+    g = torch.empty(R, N2 // 2, dtype=bf16, device=x.device)
+    with _timed("gemm", 2.0 * R * N2 * K, "flop"):
+        _lib.check(lib.egom2p_gemm_swiglu_fwd(_p(x), _p(w13), R, N2, K, x.stride(0), w13.stride(0), _p(ab), ab.stride(0), _p(g),
+                                              g.stride(0), _s()), "gemm_swiglu_fwd")
+    return ab, g
+
+
+def gemm_swiglu_bwd(dy: torch.Tensor, w2: torch.Tensor, ab: torch.Tensor):
+    """dab = swiglu'(ab) applied to dg = dy @ w2 inside the dgrad epilogue; w2 is (K, hidden) bf16."""
+    lib = _lib.load()
+    R, K = dy.shape
+    hidden = w2.shape[1]
+    dab = torch.empty(R, 2 * hidden, dtype=bf16, device=dy.device)
+    with _timed("gemm", 2.0 * R * hidden * K, "flop"):
+        _lib.check(lib.egom2p_gemm_swiglu_bwd(_p(dy), _p(w2), _p(ab), R, hidden, K, dy.stride(0), w2.stride(0), ab.stride(0),
+                                              _p(dab), dab.stride(0), _s()), "gemm_swiglu_bwd")
+    return dab
+
+
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, *, bias=None, addend=None, out_dtype=bf16):
     """y = x @ w^T, x (R,K) bf16, w (N,K) bf16."""
     R, K = x.shape

@@ -104,6 +104,17 @@ int egom2p_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N,
                      int32_t a_mn, int32_t b_mn, const float* bias, const float* addend, int64_t ld_add,
                      uint16_t* c_bf16, float* c_f32, int64_t ldc, void* stream);
 
+/* SwiGLU MLP with the gate fused into the GEMM epilogues (egom2p/models/egom2p_utils.py:154-169). W13 holds the rows of
+ * fc1 and fc3 interleaved in groups of 32 (rows [64g, 64g+32) = fc1[32g..], rows [64g+32, 64g+64) = fc3[32g..]), so a
+ * 64-column accumulator group is [a | b] of the same 32 hidden units.
+ *   fwd: ab (M, N2) bf16 = X W13^T (saved for backward) and g (M, N2/2) bf16 = silu(a) * b, in one pass.
+ *   bwd: dg = dY W2 (W2 stored (K, hidden), consumed MN-major) never leaves TMEM: dab (M, 2*hidden) bf16 =
+ *        [dg * b * silu'(a) | dg * silu(a)] in the same interleaved layout. */
+int egom2p_gemm_swiglu_fwd(const uint16_t* X, const uint16_t* W13, int32_t M, int32_t N2, int32_t K, int64_t ldx, int64_t ldw,
+                           uint16_t* ab, int64_t ld_ab, uint16_t* g, int64_t ldg, void* stream);
+int egom2p_gemm_swiglu_bwd(const uint16_t* dY, const uint16_t* W2, const uint16_t* ab, int32_t M, int32_t hidden, int32_t K,
+                           int64_t ldy, int64_t ldw, int64_t ld_ab, uint16_t* dab, int64_t ld_dab, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (4) Vocabulary head fused with softmax cross-entropy (egom2p/models/decoder_embeddings.py:489-500,
  * egom2p_model.py:614-644): logits = Y W^T are produced tile-by-tile in TMEM and never written to HBM.
