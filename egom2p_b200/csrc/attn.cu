@@ -328,7 +328,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace egom2p
 
-extern "C" int egom2p_attn_lse_stride(int32_t Mq) { return egom2p::pad64(Mq); }
+extern "C" int egom2p_attn_lse_stride(int32_t Mq) { return egom2p::padS(Mq); }
 extern "C" int64_t egom2p_attn_ranges_bytes(int32_t B, int32_t Mq) { return egom2p::range_meta_bytes(B, Mq); }
 
 extern "C" int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, int32_t B, int32_t Mq, int32_t Nk, float scale,
@@ -337,7 +337,7 @@ extern "C" int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, 
   EGO_REQUIRE(meta && B > 0 && Mq > 0 && Nk >= 0, "attn_ranges: bad argument");
   EGO_REQUIRE((key_lo == nullptr) == (key_hi == nullptr), "attn_ranges: key_lo / key_hi must both be given or both NULL");
   EGO_REQUIRE(((uintptr_t)meta & 255) == 0, "attn_ranges: meta must be 256-byte aligned");
-  const int S = pad64(Mq);
+  const int S = padS(Mq);
   RangeMeta m = carve_meta(meta, B, Mq);
   attn_rows_kernel<<<(unsigned)(((int64_t)B * S + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key_lo, key_hi, B, Mq, Nk, S,
                                                                                            scale * kLog2e, m);
@@ -354,7 +354,7 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
   EGO_REQUIRE(Q && O && meta && B > 0 && H > 0 && Mq > 0 && Nk >= 0, "attn_fwd: bad argument");
   EGO_REQUIRE(ldo % 8 == 0 && ((uintptr_t)O & 15) == 0, "attn_fwd: O must be 16-byte aligned with ldo %% 8 == 0");
   AttnFwdParams p{};
-  p.B = B; p.H = H; p.Mq = Mq; p.Nk = Nk; p.S = pad64(Mq);
+  p.B = B; p.H = H; p.Mq = Mq; p.Nk = Nk; p.S = padS(Mq);
   p.meta = carve_meta(const_cast<void*>(meta), B, Mq);
   p.O = O; p.ldo = ldo; p.lse2 = lse;
   CUtensorMap tmQ, tmK, tmV;

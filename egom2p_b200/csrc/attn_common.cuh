@@ -38,7 +38,7 @@ __device__ __forceinline__ void pair_sync(int quarter) {  // the two warps that 
 }
 
 // Range metadata of one (plan, attention kind): built once per forward by egom2p_attn_ranges, shared by all layers,
-// heads and by forward + backward. S = Mq rounded up to 64.
+// heads and by forward + backward. S = Mq rounded up to 128.
 struct RangeMeta {
   int32_t* row_lo;      // (B, S) effective key range per query row; rows >= Mq: empty
   int32_t* row_hi;      // (B, S)
@@ -48,14 +48,14 @@ struct RangeMeta {
   int32_t* blk_lo_max;  // (B, S/64) intersection (INT_MAX / INT_MIN if the block holds a uniform or padding row)
   int32_t* blk_hi_min;
 };
-static inline int pad64(int x) { return (x + 63) / 64 * 64; }
+static inline int padS(int x) { return (x + 127) / 128 * 128; }  // row-metadata / lse stride: whole 128-row tiles
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 static inline int64_t range_meta_bytes(int B, int Mq) {
-  const int64_t S = pad64(Mq);
+  const int64_t S = padS(Mq);
   return 3 * align256((int64_t)B * S * 4) + 4 * align256((int64_t)B * (S / 64) * 4);
 }
 static inline RangeMeta carve_meta(void* base, int B, int Mq) {
-  const int64_t S = pad64(Mq);
+  const int64_t S = padS(Mq);
   const int64_t rows = align256((int64_t)B * S * 4), blks = align256((int64_t)B * (S / 64) * 4);
   char* p = reinterpret_cast<char*>(base);
   RangeMeta m;

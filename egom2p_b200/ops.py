@@ -294,7 +294,7 @@ def ce_dlogits(y, w, target, lse, gscale: torch.Tensor, v0: int, vc: int, out: t
 
 # ----------------------------------------------------------------------------------------------- attention
 def lse_stride(Mq: int) -> int:
-    return (Mq + 63) // 64 * 64
+    return int(_lib.load().egom2p_attn_lse_stride(Mq))
 
 
 def attn_ranges(B, Mq, Nk, key_lo=None, key_hi=None, scale=None, device=None):

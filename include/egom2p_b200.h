@@ -140,7 +140,7 @@ int egom2p_ce_dlogits(const uint16_t* Y, const uint16_t* W, const int64_t* targe
  * (encoder key padding, decoder cross, decoder per-modality self-attention, causal). An empty range reproduces the
  * reference's masked_fill(-finfo.max) behaviour: uniform attention over all Nk keys.
  * ------------------------------------------------------------------------------------------------ */
-int egom2p_attn_lse_stride(int32_t Mq);                 /* S = Mq rounded up to 64 */
+int egom2p_attn_lse_stride(int32_t Mq);                 /* S = Mq rounded up to 128 */
 int64_t egom2p_attn_ranges_bytes(int32_t B, int32_t Mq); /* bytes of the range metadata buffer */
 /* Builds the per-row / per-block range metadata once per forward; it is shared by every layer and head and by the
  * forward and backward kernels. key_lo / key_hi are (B, Mq) int32 or both NULL. meta: 256-byte aligned. */
@@ -150,7 +150,7 @@ int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, int32_t B, 
 int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, int32_t B, int32_t H, int32_t Mq, int32_t Nk,
                     int64_t ldq, int64_t ldk, int64_t ldv, const void* meta, uint16_t* O, int64_t ldo, float* lse,
                     void* stream);
-/* Bytes of device scratch egom2p_attn_bwd needs (per-row delta terms). */
+/* Bytes of device scratch egom2p_attn_bwd needs (per-row delta terms + the fp32 dQ accumulator). */
 int64_t egom2p_attn_bwd_scratch_bytes(int32_t B, int32_t H, int32_t Mq);
 /* dQ/dK/dV use the same addressing as Q/K/V with their own row pitches; dO shares O's pitch. */
 int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, const uint16_t* O, const uint16_t* dO,

@@ -94,4 +94,4 @@ def test_c_abi_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert _lib.load().egom2p_abi_version() == 1
-    assert _lib.load().egom2p_attn_lse_stride(2048) == 2048 and _lib.load().egom2p_attn_lse_stride(20) == 64
+    assert _lib.load().egom2p_attn_lse_stride(2048) == 2048 and _lib.load().egom2p_attn_lse_stride(20) == 128
