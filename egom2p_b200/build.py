@@ -15,6 +15,8 @@ SOURCES = ["capi.cu", "plan.cu", "embed.cu", "norm.cu", "elementwise.cu", "gemm.
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("EGOM2P_TRACE"):  # debug build: clock stamps inside the attention kernels (tools/trace_attn.py)
+    FLAGS.append("-DEGOM2P_TRACE")
 
 
 def _stamp(path: str) -> str:

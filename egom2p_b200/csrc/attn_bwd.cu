@@ -1,26 +1,31 @@
 // Backward of the range-masked flash attention (see attn.cu for the forward and attn_common.cuh for the metadata).
 //
 // One fused kernel: a CTA owns one tile of 128 keys of one (batch, head) and walks the 128-query blocks that can see
-// it. Per block, five tcgen05 MMAs (all M = 128):
-//     S  = Q K^T          (TMEM)        dP = dO V^T        (TMEM)
-//     P  = exp2(S*c - lse), dS = P * (dP*scale - delta*scale)   (math warps: TMEM -> registers -> bf16 swizzled smem)
-//     dV += P^T dO        (TMEM, A = P  read MN-major)
-//     dK += dS^T Q        (TMEM, A = dS read MN-major)
-//     dQ  = dS K          (TMEM, A = dS read K-major) -> drained to an fp32 accumulator in HBM by TMA reduce-add
+// it. Keys sit on the TMEM lanes. Per block, five tcgen05 MMAs (all M = 128):
+//     S^T  = K Q^T         (TMEM fp32)        dP^T = V dO^T       (TMEM fp32)
+//     P^T  = exp2(S^T*c - lse_q), dS^T = P^T * (dP^T*scale - delta_q*scale)       (math warps)
+//     dV  += P^T dO        A = P^T  read from TMEM (bf16, written with tcgen05.st)
+//     dK  += dS^T Q        A = dS^T read from TMEM (written in place over the dP^T columns)
+//     dQ   = dS K          A = dS^T read MN-major from swizzled smem -> TMEM -> fp32 accumulator in HBM (TMA reduce-add)
 // so S and dP are produced once per (key tile, query block) pair (10 tile-GEMM units instead of 14 for separate
-// dQ / dKV kernels). Query rows sit on the TMEM lanes, so lse / delta / the key range are per-thread constants.
+// dQ / dKV kernels), and only dS touches shared memory: the kernel is bound by shared-memory bandwidth (MMA operand
+// reads), so P^T / dS^T as TMEM operands matter more than instruction count.
 //
 // 14 warps, 1 CTA / SM:
-//   warps 0-7   math: warp w handles TMEM lane quarter w&3 (32 query rows) x key half (w>>2) (64 of the 128 columns)
+//   warps 0-7   math: warp w handles TMEM lane quarter w&3 (32 keys) x query half w>>2 (64 of the 128 columns)
 //   warps 8-11  dQ drain: TMEM -> smem box -> cp.reduce.async.bulk.tensor (fp32 add), one 32-row quarter each
-//   warp 12     TMA producer (K/V once, then the Q / dO / row-metadata ring);  warp 13: MMA issuer + TMEM owner
+//   warp 12     TMA producer (K/V once, then the Q / dO / row-metadata ring)
+//   warp 13     MMA issuer A (S^T, dP^T, dQ) + TMEM owner;  warp 14: MMA issuer B (dV, dK)
 // A small pre-pass computes -delta*scale = -scale*rowsum(dO*O) and zeroes the dQ accumulator; a post-pass rounds the
 // accumulator to bf16 into the caller's dQ.
 #include "attn_common.cuh"
 
 namespace egom2p {
 
-constexpr int kBwdThreads = 448;
+constexpr int kBwdMathWarps = 8;
+constexpr int kBwdThreads = 32 * (kBwdMathWarps + 7);
+constexpr int kDrainWarp0 = kBwdMathWarps, kBwdTmaWarp = kBwdMathWarps + 4, kBwdMmaWarp = kBwdMathWarps + 5,
+              kBwdMmaWarpB = kBwdMathWarps + 6;
 constexpr int kBwdStages = 3;
 constexpr int kBwdMetaBytes = 5 * kT * 4;  // lse2, -delta*scale, lo, hi, row scale for 128 query rows
 constexpr int kMaxQBlocks = 1024;
@@ -30,6 +35,7 @@ struct BwdParams {
   RangeMeta meta;
   const float* lse2;    // (B, H, S)
   const float* ndelta;  // (B, H, S)  -delta * scale (natural-log units)
+  float scale_log2;     // scale * log2(e) of normal rows
   uint16_t* dK;
   uint16_t* dV;
   int64_t lddk, lddv;
@@ -37,21 +43,50 @@ struct BwdParams {
 struct BwdSmem {
   static constexpr int kTile = kT * 128;  // 128 rows x 64 bf16
   static constexpr int kK = 0, kV = kK + kTile, kQ = kV + kTile, kDO = kQ + kBwdStages * kTile,
-                       kP = kDO + kBwdStages * kTile,  // [128 q][2 blocks of 64 keys]: block stride kTile
-                       kDS = kP + 2 * kTile, kBox = kDS + 2 * kTile,  // 4 drain warps x 4 KB (32 rows x 32 fp32)
-                       kMeta = kBox + 4 * 4096, kList = kMeta + kBwdStages * kBwdMetaBytes,
+                       kDS = kDO + kBwdStages * kTile,  // dS^T: [128 keys][2 blocks of 64 queries], block stride kTile
+                       kBox = kDS + 2 * kTile,          // 4 drain warps x 2 boxes x 4 KB (32 rows x 32 fp32)
+                       kMeta = kBox + 8 * 4096, kList = kMeta + kBwdStages * kBwdMetaBytes,
                        kBar = kList + kMaxQBlocks * 2, kTotal = kBar + 256 + 1024;
 };
 static_assert(BwdSmem::kTotal <= 232448, "attention backward exceeds the 227 KB shared memory of one CTA");
 
 
-// Applies the row's key range to 32 raw scores whose first key index is kv: masked -> -inf, uniform rows -> 0.
-__device__ __forceinline__ void mask_scores(uint32_t (&s)[32], int kv, int lo, int hi, float rscale) {
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const bool ok = (kv + c >= lo) && (kv + c < hi);
-    s[c] = ok ? (rscale != 0.f ? s[c] : 0u) : 0xff800000u;
-  }
+#ifdef EGOM2P_TRACE
+// Debug build only (python -m egom2p_b200.build with EGOM2P_TRACE=1): per-iteration clock stamps of CTA (0,0,0).
+__device__ long long g_trace[16 * 64];
+#define TRACE(slot, idx)                                                                          \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 64 && (threadIdx.x & 31) == 0) \
+      g_trace[(slot) * 64 + (idx)] = clock64();                                                   \
+  } while (0)
+#else
+#define TRACE(slot, idx) do {} while (0)
+#endif
+
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 16 bf16 (8 columns of packed pairs), issued by ONE thread.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_f4(const void* p) {  // 16-byte shared load (a warp-wide broadcast when p is uniform)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -61,7 +96,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sK = smem + BwdSmem::kK, *sV = smem + BwdSmem::kV, *sQ = smem + BwdSmem::kQ, *sDO = smem + BwdSmem::kDO,
-          *sP = smem + BwdSmem::kP, *sDS = smem + BwdSmem::kDS, *sBox = smem + BwdSmem::kBox, *sMeta = smem + BwdSmem::kMeta;
+          *sDS = smem + BwdSmem::kDS, *sBox = smem + BwdSmem::kBox, *sMeta = smem + BwdSmem::kMeta;
   uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + BwdSmem::kList);  // bit 15: no masking needed for this block
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBar);
   uint64_t* kv_full = bars;                    // K / V tile landed
@@ -70,7 +105,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = q_empty + kBwdStages;     // S in TMEM
   uint64_t* s_free = s_full + 1;               // math warps hold S in registers
   uint64_t* dp_full = s_free + 1;
-  uint64_t* dp_free = dp_full + 1;
+  uint64_t* dp_free = dp_full + 1;             // (here: dK MMA retired -> the dP^T / dS^T columns may be overwritten)
   uint64_t* p_full = dp_free + 1;              // P in smem
   uint64_t* p_empty = p_full + 1;              // dV MMA retired
   uint64_t* ds_full = p_empty + 1;             // dS in smem
@@ -87,10 +122,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < kBwdStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    mbar_init(s_full, 1);   mbar_init(s_free, kAttnComputeWarps);
-    mbar_init(dp_full, 1);  mbar_init(dp_free, kAttnComputeWarps);
-    mbar_init(p_full, kAttnComputeWarps);  mbar_init(p_empty, 1);
-    mbar_init(ds_full, kAttnComputeWarps); mbar_init(ds_empty, 1);
+    mbar_init(s_full, 1);   mbar_init(s_free, kBwdMathWarps);
+    mbar_init(dp_full, 1);  mbar_init(dp_free, 1);
+    mbar_init(p_full, kBwdMathWarps);  mbar_init(p_empty, 1);
+    mbar_init(ds_full, kBwdMathWarps); mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);  mbar_init(dq_free, 4);
     mbar_init(dkv_full, 1);
     fence_mbar_init();
@@ -114,16 +149,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (lane == 0) *s_n = n < kMaxQBlocks ? n : kMaxQBlocks;
   }
-  if (warp == 13) tmem_alloc<512>(tmem_slot);
+  if (warp == kBwdMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n = *s_n;
-  constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 320, cDQ = 384;  // TMEM columns
+  constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 320, cDQ = 384, cPT = 448;  // TMEM columns (cPT: P^T as bf16 pairs)
 
-  if (warp >= 12) {
-    if (warp == 12) {
+  if (warp >= kBwdTmaWarp) {
+    if (warp == kBwdTmaWarp) {
       // ------------------------------------------------------------------------------------------ TMA producer
       if (n > 0) {
         if (elect_one()) {
@@ -151,26 +186,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           __syncwarp();
         }
       }
-    } else if (warp == 13) {
+    } else if (warp == kBwdMmaWarp) {
       // ------------------------------------------------------------------------------------------ MMA issuer
       if (n > 0) {
-        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kT, 0, 0);    // S, dP: K-major x K-major, N = 128
-        constexpr uint32_t idesc_mm = umma_idesc_bf16(128, kD, 1, 1);    // dV, dK: MN-major x MN-major, N = 64
-        constexpr uint32_t idesc_km = umma_idesc_bf16(128, kD, 0, 1);    // dQ: K-major x MN-major, N = 64
+        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kT, 0, 0);    // S^T, dP^T: K-major x K-major, N = 128
+        constexpr uint32_t idesc_tm = umma_idesc_bf16(128, kD, 0, 1);    // dV, dK: A in TMEM x MN-major B, N = 64
+        constexpr uint32_t idesc_mm = umma_idesc_bf16(128, kD, 1, 1);    // dQ: MN-major x MN-major, N = 64
         const uint32_t tS = tmem_base + cS, tDP = tmem_base + cDP, tDV = tmem_base + cDV, tDK = tmem_base + cDK,
-                       tDQ = tmem_base + cDQ;
+                       tDQ = tmem_base + cDQ, tPT = tmem_base + cPT;
         const uint64_t dK0 = umma_desc_kmajor_sw128(smem_u32(sK)), dV0 = umma_desc_kmajor_sw128(smem_u32(sV));
         const uint64_t dKm0 = umma_desc_mnmajor_sw128(smem_u32(sK), 8192);
-        const uint64_t dPm0 = umma_desc_mnmajor_sw128(smem_u32(sP), BwdSmem::kTile);
         const uint64_t dDSm0 = umma_desc_mnmajor_sw128(smem_u32(sDS), BwdSmem::kTile);
-        const uint64_t dDSk0 = umma_desc_kmajor_sw128(smem_u32(sDS));
-        const uint64_t dDSk1 = umma_desc_kmajor_sw128(smem_u32(sDS + BwdSmem::kTile));
         auto issue_s = [&](int st) {
           const uint64_t dQ0 = umma_desc_kmajor_sw128(smem_u32(sQ + st * BwdSmem::kTile));
           if (elect_one()) {
-            umma_bf16_ss(tS, dQ0, dK0, idesc_kk, 0u);
+            umma_bf16_ss(tS, dK0, dQ0, idesc_kk, 0u);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_bf16_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_kk, 1u);
+            for (int k = 1; k < 4; ++k) umma_bf16_ss(tS, dK0 + 2 * k, dQ0 + 2 * k, idesc_kk, 1u);
             umma_commit(s_full);
           }
           __syncwarp();
@@ -178,194 +210,248 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto issue_dp = [&](int st) {
           const uint64_t dDO0 = umma_desc_kmajor_sw128(smem_u32(sDO + st * BwdSmem::kTile));
           if (elect_one()) {
-            umma_bf16_ss(tDP, dDO0, dV0, idesc_kk, 0u);
+            umma_bf16_ss(tDP, dV0, dDO0, idesc_kk, 0u);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_bf16_ss(tDP, dDO0 + 2 * k, dV0 + 2 * k, idesc_kk, 1u);
+            for (int k = 1; k < 4; ++k) umma_bf16_ss(tDP, dV0 + 2 * k, dDO0 + 2 * k, idesc_kk, 1u);
             umma_commit(dp_full);
           }
           __syncwarp();
         };
+        // One issuing thread sustains one tcgen05.mma per ~60 cycles whatever N <= 128 is (tools/micro/bench_umma.cu), so the
+        // 32 MMAs of a block are split over two issuer warps: this one S^T, dP^T and dQ, warp B dV and dK. MMAs of
+        // different issuers are not ordered against each other: every cross dependency goes through an mbarrier.
         mbar_wait(kv_full, 0);
         mbar_wait(&q_full[0], 0);
         tc_fence_after();
         issue_s(0);
         issue_dp(0);
         for (int idx = 0; idx < n; ++idx) {
-          const int st = idx % kBwdStages, st1 = (idx + 1) % kBwdStages;
+          const int st1 = (idx + 1) % kBwdStages;
           const uint32_t par = idx & 1;
-          if (idx + 1 < n) {  // S of the next block as soon as this block's scores sit in registers
+          if (idx + 1 < n) {  // S^T of the next block as soon as this block's scores sit in registers
             mbar_wait(&q_full[st1], ((idx + 1) / kBwdStages) & 1);
             mbar_wait(s_free, par);
             tc_fence_after();
+            TRACE(0, idx);
             issue_s(st1);
           }
-          // dV += P^T dO
+          // dQ = dS K (A = dS^T in smem, read MN-major)
+          mbar_wait(ds_full, par);
+          if (idx > 0) mbar_wait(dq_free, (idx - 1) & 1);
+          tc_fence_after();
+          TRACE(4, idx);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_bf16_ss(tDQ, dDSm0 + 128 * k, dKm0 + 128 * k, idesc_mm, k ? 1u : 0u);
+            umma_commit(dq_full);
+            umma_commit(ds_empty);
+          }
+          __syncwarp();
+          if (idx + 1 < n) {  // dP^T of the next block once warp B's dK MMA has consumed dS^T from the same columns
+            mbar_wait(dp_free, par);
+            tc_fence_after();
+            TRACE(2, idx);
+            issue_dp(st1);
+          }
+        }
+      }
+    } else if (warp == kBwdMmaWarpB) {
+      // ------------------------------------------------------------------------------------------ MMA issuer B: dV, dK
+      if (n > 0) {
+        constexpr uint32_t idesc_tm = umma_idesc_bf16(128, kD, 0, 1);    // A in TMEM x MN-major B, N = 64
+        const uint32_t tDP = tmem_base + cDP, tDV = tmem_base + cDV, tDK = tmem_base + cDK, tPT = tmem_base + cPT;
+        for (int idx = 0; idx < n; ++idx) {
+          const int st = idx % kBwdStages;
+          const uint32_t par = idx & 1;
+          // dV += P^T dO  (A: 8 k-steps of 16 queries = 8 TMEM columns each)
           mbar_wait(p_full, par);
           tc_fence_after();
+          TRACE(1, idx);
           const uint64_t dDOm0 = umma_desc_mnmajor_sw128(smem_u32(sDO + st * BwdSmem::kTile), 8192);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_bf16_ss(tDV, dPm0 + 128 * k, dDOm0 + 128 * k, idesc_mm, (idx | k) ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) umma_bf16_ts(tDV, tPT + 8 * k, dDOm0 + 128 * k, idesc_tm, (idx | k) ? 1u : 0u);
             umma_commit(p_empty);
           }
           __syncwarp();
-          if (idx + 1 < n) {
-            mbar_wait(dp_free, par);
-            tc_fence_after();
-            issue_dp(st1);
-          }
-          // dK += dS^T Q ; dQ = dS K
+          // dK += dS^T Q (A = dS^T, written in place over each thread's own dP^T columns: k-steps 0-3 at columns 0-31,
+          // 4-7 at columns 64-95)
           mbar_wait(ds_full, par);
           tc_fence_after();
+          TRACE(3, idx);
           const uint64_t dQm0 = umma_desc_mnmajor_sw128(smem_u32(sQ + st * BwdSmem::kTile), 8192);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_bf16_ss(tDK, dDSm0 + 128 * k, dQm0 + 128 * k, idesc_mm, (idx | k) ? 1u : 0u);
-            umma_commit(&q_empty[st]);
-          }
-          __syncwarp();
-          if (idx > 0) {
-            mbar_wait(dq_free, (idx - 1) & 1);
-            tc_fence_after();
-          }
-          if (elect_one()) {
-#pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16_ss(tDQ, (k < 4 ? dDSk0 : dDSk1) + 2 * (k & 3), dKm0 + 128 * k, idesc_km, k ? 1u : 0u);
-            umma_commit(dq_full);
-            umma_commit(ds_empty);
+              umma_bf16_ts(tDK, tDP + (k < 4 ? 8 * k : 64 + 8 * (k - 4)), dQm0 + 128 * k, idesc_tm, (idx | k) ? 1u : 0u);
+            umma_commit(&q_empty[st]);
+            umma_commit(dp_free);
             if (idx == n - 1) umma_commit(dkv_full);
           }
           __syncwarp();
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= kDrainWarp0) {
     // -------------------------------------------------------------------------------------------- dQ drain
     const int quarter = warp & 3;
-    uint8_t* box = sBox + quarter * 4096;
+    uint8_t* box0 = sBox + quarter * 8192;
     const uint32_t t_dq = tmem_base + ((uint32_t)(quarter * 32) << 16) + cDQ;
     for (int idx = 0; idx < n; ++idx) {
       const int r0 = (int)(s_list[idx] & 0x7fff) * kT + quarter * 32;  // first query row (within the sample) of this box
       mbar_wait(dq_full, idx & 1);
       tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld32(t_dq, v0);
-      tmem_ld32(t_dq + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
+      if (warp == kDrainWarp0) TRACE(11, idx);
+      const bool live = r0 < p.Mq;  // warp-uniform: rows past the sample's last query are skipped
+      if (lane == 0) tma_store_wait_read();  // the previous block's reduces have finished reading both boxes
       __syncwarp();
-      if (lane == 0) mbar_arrive(dq_free);
-      if (r0 >= p.Mq) continue;  // warp-uniform: rows past the sample's last query
 #pragma unroll
       for (int hb = 0; hb < 2; ++hb) {
-        if (lane == 0) tma_store_wait_read();  // the previous reduce has finished reading the box
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t* v = hb ? v1 : v0;
-          *reinterpret_cast<uint4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        uint32_t v[32];
+        uint8_t* box = box0 + hb * 4096;
+        tmem_ld32(t_dq + hb * 32, v);
+        tmem_ld_wait();
+        if (hb == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
         }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_reduce_add_2d(&tmDQ, box, h * kD + hb * 32, b * p.Mq + r0);
-          tma_store_commit();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmDQ, box, h * kD + hb * 32, b * p.Mq + r0);
+            tma_store_commit();
+          }
         }
       }
+      if (warp == kDrainWarp0) TRACE(12, idx);
     }
     if (lane == 0) tma_store_wait_all();
   } else {
     // -------------------------------------------------------------------------------------------- math warps
-    const int quarter = warp & 3, half = warp >> 2;
-    const int trow = quarter * 32 + lane;
+    const int quarter = warp & 3, half = warp >> 2;  // half: which 64 of the block's 128 queries (TMEM columns)
+    const int trow = quarter * 32 + lane;            // key row inside the tile == TMEM lane
+    const int kidx = kv0 + trow;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int kcol0 = kv0 + half * 64;  // first key of this thread's 64 columns
-    uint8_t* pP = sP + half * BwdSmem::kTile;
     uint8_t* pDS = sDS + half * BwdSmem::kTile;
+    const float SC = p.scale_log2, RN = p.scale_log2 * kLn2;
     for (int idx = 0; idx < n; ++idx) {
       const int st = idx % kBwdStages;
       const uint32_t par = idx & 1;
-      const uint16_t item = s_list[idx];
-      const bool inside = (item & 0x8000) != 0;
-      const int qrow = (int)(item & 0x7fff) * kT + trow;
-      mbar_wait(&q_full[st], (idx / kBwdStages) & 1);  // row metadata visible
-      const float* mf = reinterpret_cast<const float*>(sMeta + st * kBwdMetaBytes);
-      const int* mi = reinterpret_cast<const int*>(mf);
-      const bool row_ok = qrow < p.Mq;
-      const float nlse = row_ok ? -mf[trow] : -INFINITY;
-      const float ndl = mf[kT + trow];
-      const int lo = mi[2 * kT + trow], hi = mi[3 * kT + trow];
-      const float rscale = mf[4 * kT + trow];
-      const float rs_nat = rscale * kLn2;
-      // ---- P = exp2(S * c - lse), kept as packed bf16 pairs (the values the dV MMA consumes)
+      const bool inside = (s_list[idx] & 0x8000) != 0;
+      // per-query metadata of this thread's 64 columns (warp-uniform addresses: broadcast loads)
+      const float* m_ls = reinterpret_cast<const float*>(sMeta + st * kBwdMetaBytes) + half * 64;
+      const float* m_nd = m_ls + kT;
+      const int* m_lo = reinterpret_cast<const int*>(m_ls + 2 * kT);
+      const int* m_hi = m_lo + kT;
+      const float* m_rs = m_ls + 4 * kT;
       uint32_t pp[32];
+      // ---- P^T = exp2(S^T * c - lse_q) as packed bf16 pairs
       {
         uint32_t s0[32], s1[32];
+        if (warp == 0) TRACE(5, idx);
+        mbar_wait(&q_full[st], (idx / kBwdStages) & 1);  // row metadata visible
         mbar_wait(s_full, par);
         tc_fence_after();
+        if (warp == 0) TRACE(6, idx);
         tmem_ld32(t_lane + cS + half * 64, s0);
         tmem_ld32(t_lane + cS + half * 64 + 32, s1);
+        if (idx > 0) mbar_wait(p_empty, (idx - 1) & 1);  // dV MMA of the previous block retired: the P^T columns are free
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free);
-        float sc = rscale;
-        if (!inside) {
-          if (!(rscale != 0.f && kcol0 >= lo && kcol0 + 64 <= hi)) {
-            sc = rscale != 0.f ? rscale : 1.f;
-            mask_scores(s0, kcol0, lo, hi, rscale);
-            mask_scores(s1, kcol0 + 32, lo, hi, rscale);
+        if (inside) {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 la = lds_f4(m_ls + 4 * c4), lb = lds_f4(m_ls + 32 + 4 * c4);
+            pp[2 * c4] = pack_bf16(ex2(fmaf(__uint_as_float(s0[4 * c4]), SC, -la.x)), ex2(fmaf(__uint_as_float(s0[4 * c4 + 1]), SC, -la.y)));
+            pp[2 * c4 + 1] = pack_bf16(ex2(fmaf(__uint_as_float(s0[4 * c4 + 2]), SC, -la.z)), ex2(fmaf(__uint_as_float(s0[4 * c4 + 3]), SC, -la.w)));
+            pp[16 + 2 * c4] = pack_bf16(ex2(fmaf(__uint_as_float(s1[4 * c4]), SC, -lb.x)), ex2(fmaf(__uint_as_float(s1[4 * c4 + 1]), SC, -lb.y)));
+            pp[16 + 2 * c4 + 1] = pack_bf16(ex2(fmaf(__uint_as_float(s1[4 * c4 + 2]), SC, -lb.z)), ex2(fmaf(__uint_as_float(s1[4 * c4 + 3]), SC, -lb.w)));
+          }
+        } else {  // block touches a range boundary, a uniform (fully masked) row or padding rows
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float e[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int q = 2 * c + u;
+              const float rs = m_rs[q];
+              const bool ok = kidx >= m_lo[q] && kidx < m_hi[q];
+              const float sv = __uint_as_float(q < 32 ? s0[q & 31] : s1[q & 31]);
+              e[u] = ok ? ex2(fmaf(rs != 0.f ? sv : 0.f, rs, -m_ls[q])) : 0.f;
+            }
+            pp[c] = pack_bf16(e[0], e[1]);
           }
         }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          pp[c] = pack_bf16(ex2(fmaf(__uint_as_float(s0[2 * c]), sc, nlse)), ex2(fmaf(__uint_as_float(s0[2 * c + 1]), sc, nlse)));
-          pp[16 + c] = pack_bf16(ex2(fmaf(__uint_as_float(s1[2 * c]), sc, nlse)), ex2(fmaf(__uint_as_float(s1[2 * c + 1]), sc, nlse)));
-        }
       }
-      if (idx > 0) mbar_wait(p_empty, (idx - 1) & 1);
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8)
-        *reinterpret_cast<uint4*>(pP + swz_off(trow, c8)) = make_uint4(pp[4 * c8], pp[4 * c8 + 1], pp[4 * c8 + 2], pp[4 * c8 + 3]);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      // ---- dS = P * (dP * scale - delta * scale), 32 columns at a time
+      if (warp == 0) TRACE(7, idx);
+      tmem_st32(t_lane + cPT + half * 32, pp);   // (p_empty of the previous block was awaited under the S^T load)
+      // dP^T of this block has been in TMEM for a while: start its load while the P^T store drains
+      uint32_t d0[32];
       mbar_wait(dp_full, par);
       tc_fence_after();
+      tmem_ld32(t_lane + cDP + half * 64, d0);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (warp == 0) TRACE(8, idx);
+      // ---- dS^T = P^T * (dP^T * scale - delta_q * scale): the bracket in fp32, the product as one bf16x2 multiply per pair
+      auto dsmul = [&](const uint32_t (&d)[32], int hh) {
+        if (inside) {  // straight-line: the eight metadata loads are issued back to back
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t d[32], ds[16];
-        tmem_ld32(t_lane + cDP + half * 64 + hh * 32, d);
-        tmem_ld_wait();
-        if (hh == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dp_free);
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 nd = lds_f4(m_nd + hh * 32 + 4 * c4);
+            const uint32_t t0 = pack_bf16(fmaf(__uint_as_float(d[4 * c4]), RN, nd.x), fmaf(__uint_as_float(d[4 * c4 + 1]), RN, nd.y));
+            const uint32_t t1 = pack_bf16(fmaf(__uint_as_float(d[4 * c4 + 2]), RN, nd.z), fmaf(__uint_as_float(d[4 * c4 + 3]), RN, nd.w));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(pp[hh * 16 + 2 * c4]) : "r"(pp[hh * 16 + 2 * c4]), "r"(t0));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(pp[hh * 16 + 2 * c4 + 1]) : "r"(pp[hh * 16 + 2 * c4 + 1]), "r"(t1));
+          }
+        } else {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 nd = lds_f4(m_nd + hh * 32 + 4 * c4);
+            const float4 rs = lds_f4(m_rs + hh * 32 + 4 * c4);
+            const uint32_t t0 = pack_bf16(fmaf(__uint_as_float(d[4 * c4]), rs.x * kLn2, nd.x), fmaf(__uint_as_float(d[4 * c4 + 1]), rs.y * kLn2, nd.y));
+            const uint32_t t1 = pack_bf16(fmaf(__uint_as_float(d[4 * c4 + 2]), rs.z * kLn2, nd.z), fmaf(__uint_as_float(d[4 * c4 + 3]), rs.w * kLn2, nd.w));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(pp[hh * 16 + 2 * c4]) : "r"(pp[hh * 16 + 2 * c4]), "r"(t0));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(pp[hh * 16 + 2 * c4 + 1]) : "r"(pp[hh * 16 + 2 * c4 + 1]), "r"(t1));
+          }
         }
+      };
+      tmem_ld_wait();
+      if (warp == 0) TRACE(9, idx);
+      dsmul(d0, 0);
+      if (warp == 0) TRACE(13, idx);
+      tmem_ld32(t_lane + cDP + half * 64 + 32, d0);
+      if (idx > 0) mbar_wait(ds_empty, (idx - 1) & 1);  // dQ MMA of the previous block retired: the smem copy of dS^T is free
+      tmem_ld_wait();
+      if (warp == 0) TRACE(14, idx);
+      dsmul(d0, 1);
+      if (warp == 0) TRACE(15, idx);
+      // dS^T -> TMEM in place over this thread's own dP^T columns (all 64 are in registers), and -> smem for the dQ MMA
+      tmem_st32(t_lane + cDP + half * 64, pp);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const uint32_t w = pp[hh * 16 + c];
-          const float p0 = __uint_as_float(w << 16), p1 = __uint_as_float(w & 0xffff0000u);
-          ds[c] = pack_bf16(p0 * fmaf(__uint_as_float(d[2 * c]), rs_nat, ndl), p1 * fmaf(__uint_as_float(d[2 * c + 1]), rs_nat, ndl));
-        }
-        if (hh == 0 && idx > 0) mbar_wait(ds_empty, (idx - 1) & 1);
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8)
-          *reinterpret_cast<uint4*>(pDS + swz_off(trow, hh * 4 + c8)) = make_uint4(ds[4 * c8], ds[4 * c8 + 1], ds[4 * c8 + 2], ds[4 * c8 + 3]);
-      }
+      for (int c8 = 0; c8 < 8; ++c8)
+        *reinterpret_cast<uint4*>(pDS + swz_off(trow, c8)) = make_uint4(pp[4 * c8], pp[4 * c8 + 1], pp[4 * c8 + 2], pp[4 * c8 + 3]);
       fence_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
+      if (warp == 0) TRACE(10, idx);
     }
     // ---- epilogue: dV, dK (this thread: key row kv0 + trow, 32 of the 64 head-dim columns)
     if (n > 0) {
       mbar_wait(dkv_full, 0);
       tc_fence_after();
     }
-    const int kidx = kv0 + trow;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       uint32_t v[32];
@@ -393,7 +479,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == kBwdMmaWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -456,6 +542,12 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_cast_kernel(const float* __re
 
 }  // namespace egom2p
 
+#ifdef EGOM2P_TRACE
+extern "C" int egom2p_debug_attn_trace(long long* host_dst) {
+  return (int)cudaMemcpyFromSymbol(host_dst, egom2p::g_trace, sizeof(egom2p::g_trace));
+}
+#endif
+
 extern "C" int64_t egom2p_attn_bwd_scratch_bytes(int32_t B, int32_t H, int32_t Mq) {
   using namespace egom2p;
   return align256((int64_t)B * H * padS(Mq) * 4) + align256((int64_t)B * Mq * H * kD * 4) + 256;
@@ -466,7 +558,6 @@ extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint1
                                int64_t ldv, int64_t ldo, const void* meta, float scale, void* scratch, uint16_t* dQ,
                                uint16_t* dK, uint16_t* dV, int64_t lddq, int64_t lddk, int64_t lddv, void* stream_) {
   using namespace egom2p;
-  (void)scale;  // the per-row scale lives in the range metadata
   cudaStream_t stream = (cudaStream_t)stream_;
   EGO_REQUIRE(Q && O && dO && lse && meta && scratch && dQ && B > 0 && H > 0 && Mq > 0 && Nk >= 0, "attn_bwd: bad argument");
   EGO_REQUIRE(((uintptr_t)scratch & 255) == 0 && ((uintptr_t)lse & 255) == 0 && ((uintptr_t)meta & 255) == 0,
@@ -497,7 +588,7 @@ extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint1
     if ((rc = make_tmap_bf16_2d(&tmK, K, (uint64_t)B * Nk, (uint64_t)H * kD, ldk, kT, kD))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmV, V, (uint64_t)B * Nk, (uint64_t)H * kD, ldv, kT, kD))) return rc;
     if ((rc = make_tmap_2d(&tmDQ, dq_acc, 4, (uint64_t)B * Mq, (uint64_t)H * kD, (uint64_t)H * kD, 32, 32))) return rc;
-    BwdParams pb{B, H, Mq, Nk, S, rm, lse, ndelta, dK, dV, lddk, lddv};
+    BwdParams pb{B, H, Mq, Nk, S, rm, lse, ndelta, scale * kLog2e, dK, dV, lddk, lddv};
     attn_bwd_kernel<<<dim3((Nk + kT - 1) / kT, H, B), kBwdThreads, BwdSmem::kTotal, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, pb);
     if ((rc = check_launch("attn_bwd"))) return rc;
   }

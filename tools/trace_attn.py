@@ -1,0 +1,23 @@
+"""Debug: per-iteration timeline of CTA (0,0,0) of the fused attention backward. Needs `EGOM2P_TRACE=1 python -m egom2p_b200.build`."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from egom2p_b200 import ops, _lib
+B, H, M, D = 4, 12, 2048, 768
+qkv = torch.randn(B * M, 3 * D, device="cuda").bfloat16()
+do = torch.randn(B * M, D, device="cuda").bfloat16()
+dqkv = torch.empty_like(qkv)
+meta = ops.attn_ranges(B, M, M, device=qkv.device)
+o, lse = ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, M, M, meta=meta)
+for _ in range(2):
+    ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, B, H, M, M, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], meta=meta)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (16 * 64))()
+lib = _lib.load()
+assert lib.egom2p_debug_attn_trace(buf) == 0
+names = ["mmaA:S(j+1)", "mmaB:dV", "mmaA:dP(j+1)", "mmaB:dK", "mmaA:dQ", "math:top", "math:S ready", "math:P done", "math:P stored",
+         "math:dP0 loaded", "math:dS stored", "drain:dQ ready", "drain:done", "math:ds0 done", "math:dP1 loaded", "math:ds1 done"]
+t0 = buf[5 * 64]
+for idx in range(16):
+    ev = sorted((buf[s * 64 + idx] - t0, names[s]) for s in range(16) if buf[s * 64 + idx])
+    print("it %2d: " % idx + "  ".join("%s@%d" % (n, t) for t, n in ev))
