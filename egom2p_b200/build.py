@@ -21,7 +21,7 @@ if os.environ.get("EGOM2P_TRACE"):  # debug build: clock stamps inside the atten
 
 def _stamp(path: str) -> str:
     h = hashlib.sha1()
-    for f in [path, os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "egom2p_b200.h")]:
+    for f in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "attn_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "egom2p_b200.h")]:
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(FLAGS).encode())

@@ -97,7 +97,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sK = smem + BwdSmem::kK, *sV = smem + BwdSmem::kV, *sQ = smem + BwdSmem::kQ, *sDO = smem + BwdSmem::kDO,
           *sDS = smem + BwdSmem::kDS, *sBox = smem + BwdSmem::kBox, *sMeta = smem + BwdSmem::kMeta;
-  uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + BwdSmem::kList);  // bit 15: no masking needed for this block
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + BwdSmem::kList);  // bit 15: block needs no masking; bit 14: every
+                                                                          // row is a normal row (range masks only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBar);
   uint64_t* kv_full = bars;                    // K / V tile landed
   uint64_t* q_full = bars + 1;                 // [3] Q / dO / metadata of a query block landed
@@ -134,17 +135,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     int n = 0;
     for (int i0 = 0; i0 < nqb; i0 += 32) {
       const int i = i0 + lane;
-      bool take = false, inside = false;
+      bool take = false, inside = false, normal = false;
       if (i < nqb) {
         const int64_t o = ((int64_t)b * nqb + i) * 2;
         const int lo = min(p.meta.blk_lo[o], p.meta.blk_lo[o + 1]), hi = max(p.meta.blk_hi[o], p.meta.blk_hi[o + 1]);
         take = hi > kv0 && lo < kv0 + kT;
         inside = max(p.meta.blk_lo_max[o], p.meta.blk_lo_max[o + 1]) <= kv0 &&
                  min(p.meta.blk_hi_min[o], p.meta.blk_hi_min[o + 1]) >= kv0 + kT;
+        normal = p.meta.blk_lo_max[o] != INT_MAX && p.meta.blk_lo_max[o + 1] != INT_MAX;  // no uniform / padding row
       }
       const unsigned msk = __ballot_sync(0xffffffffu, take);
       const int pos = n + __popc(msk & ((1u << lane) - 1));
-      if (take && pos < kMaxQBlocks) s_list[pos] = (uint16_t)(i | (inside ? 0x8000 : 0));
+      if (take && pos < kMaxQBlocks) s_list[pos] = (uint16_t)(i | (inside ? 0x8000 : 0) | (normal ? 0x4000 : 0));
       n += __popc(msk);
     }
     if (lane == 0) *s_n = n < kMaxQBlocks ? n : kMaxQBlocks;
@@ -169,7 +171,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         for (int idx = 0; idx < n; ++idx) {
           const int st = idx % kBwdStages;
-          const int r0 = (int)(s_list[idx] & 0x7fff) * kT;
+          const int r0 = (int)(s_list[idx] & 0x3fff) * kT;
           mbar_wait(&q_empty[st], ((idx / kBwdStages) & 1) ^ 1);
           uint8_t* meta = sMeta + st * kBwdMetaBytes;
           const int64_t hoff = ((int64_t)b * p.H + h) * p.S + r0, roff = (int64_t)b * p.S + r0;
@@ -298,7 +300,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* box0 = sBox + quarter * 8192;
     const uint32_t t_dq = tmem_base + ((uint32_t)(quarter * 32) << 16) + cDQ;
     for (int idx = 0; idx < n; ++idx) {
-      const int r0 = (int)(s_list[idx] & 0x7fff) * kT + quarter * 32;  // first query row (within the sample) of this box
+      const int r0 = (int)(s_list[idx] & 0x3fff) * kT + quarter * 32;  // first query row (within the sample) of this box
       mbar_wait(dq_full, idx & 1);
       tc_fence_after();
       if (warp == kDrainWarp0) TRACE(11, idx);
@@ -342,7 +344,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int idx = 0; idx < n; ++idx) {
       const int st = idx % kBwdStages;
       const uint32_t par = idx & 1;
-      const bool inside = (s_list[idx] & 0x8000) != 0;
+      const bool inside = (s_list[idx] & 0x8000) != 0, normal = (s_list[idx] & 0x4000) != 0;
       // per-query metadata of this thread's 64 columns (warp-uniform addresses: broadcast loads)
       const float* m_ls = reinterpret_cast<const float*>(sMeta + st * kBwdMetaBytes) + half * 64;
       const float* m_nd = m_ls + kT;
@@ -366,13 +368,57 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free);
         if (inside) {
+          // three passes (arguments, exponentials, packing) so that no instruction waits on the one just before it: with
+          // two math warps per scheduler the MUFU latency is not hidden by other warps
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 la = lds_f4(m_ls + 4 * c4), lb = lds_f4(m_ls + 32 + 4 * c4);
-            pp[2 * c4] = pack_bf16(ex2(fmaf(__uint_as_float(s0[4 * c4]), SC, -la.x)), ex2(fmaf(__uint_as_float(s0[4 * c4 + 1]), SC, -la.y)));
-            pp[2 * c4 + 1] = pack_bf16(ex2(fmaf(__uint_as_float(s0[4 * c4 + 2]), SC, -la.z)), ex2(fmaf(__uint_as_float(s0[4 * c4 + 3]), SC, -la.w)));
-            pp[16 + 2 * c4] = pack_bf16(ex2(fmaf(__uint_as_float(s1[4 * c4]), SC, -lb.x)), ex2(fmaf(__uint_as_float(s1[4 * c4 + 1]), SC, -lb.y)));
-            pp[16 + 2 * c4 + 1] = pack_bf16(ex2(fmaf(__uint_as_float(s1[4 * c4 + 2]), SC, -lb.z)), ex2(fmaf(__uint_as_float(s1[4 * c4 + 3]), SC, -lb.w)));
+            s0[4 * c4] = __float_as_uint(fmaf(__uint_as_float(s0[4 * c4]), SC, -la.x));
+            s0[4 * c4 + 1] = __float_as_uint(fmaf(__uint_as_float(s0[4 * c4 + 1]), SC, -la.y));
+            s0[4 * c4 + 2] = __float_as_uint(fmaf(__uint_as_float(s0[4 * c4 + 2]), SC, -la.z));
+            s0[4 * c4 + 3] = __float_as_uint(fmaf(__uint_as_float(s0[4 * c4 + 3]), SC, -la.w));
+            s1[4 * c4] = __float_as_uint(fmaf(__uint_as_float(s1[4 * c4]), SC, -lb.x));
+            s1[4 * c4 + 1] = __float_as_uint(fmaf(__uint_as_float(s1[4 * c4 + 1]), SC, -lb.y));
+            s1[4 * c4 + 2] = __float_as_uint(fmaf(__uint_as_float(s1[4 * c4 + 2]), SC, -lb.z));
+            s1[4 * c4 + 3] = __float_as_uint(fmaf(__uint_as_float(s1[4 * c4 + 3]), SC, -lb.w));
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {  // one exponential in four on the FMA pipes (ex2_poly), the rest on the MUFU
+            s0[c] = __float_as_uint((c & 3) == 3 ? ex2_poly(__uint_as_float(s0[c])) : ex2(__uint_as_float(s0[c])));
+            s1[c] = __float_as_uint((c & 3) == 3 ? ex2_poly(__uint_as_float(s1[c])) : ex2(__uint_as_float(s1[c])));
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            pp[c] = pack_bf16(__uint_as_float(s0[2 * c]), __uint_as_float(s0[2 * c + 1]));
+            pp[16 + c] = pack_bf16(__uint_as_float(s1[2 * c]), __uint_as_float(s1[2 * c + 1]));
+          }
+        } else if (normal) {
+          // range boundaries cross the block but every row is a normal row: same three passes, masked arguments -> -inf
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint32_t(&sv)[32] = g ? s1 : s0;
+              const float4 l = lds_f4(m_ls + g * 32 + 4 * c4), lo = lds_f4(m_lo + g * 32 + 4 * c4), hi = lds_f4(m_hi + g * 32 + 4 * c4);
+              const float lv[4] = {l.x, l.y, l.z, l.w};
+              const int lov[4] = {__float_as_int(lo.x), __float_as_int(lo.y), __float_as_int(lo.z), __float_as_int(lo.w)};
+              const int hiv[4] = {__float_as_int(hi.x), __float_as_int(hi.y), __float_as_int(hi.z), __float_as_int(hi.w)};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const bool ok = kidx >= lov[u] && kidx < hiv[u];
+                sv[4 * c4 + u] = ok ? __float_as_uint(fmaf(__uint_as_float(sv[4 * c4 + u]), SC, -lv[u])) : 0xff800000u;
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            s0[c] = __float_as_uint(ex2(__uint_as_float(s0[c])));
+            s1[c] = __float_as_uint(ex2(__uint_as_float(s1[c])));
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            pp[c] = pack_bf16(__uint_as_float(s0[2 * c]), __uint_as_float(s0[2 * c + 1]));
+            pp[16 + c] = pack_bf16(__uint_as_float(s1[2 * c]), __uint_as_float(s1[2 * c + 1]));
           }
         } else {  // block touches a range boundary, a uniform (fully masked) row or padding rows
 #pragma unroll
@@ -404,7 +450,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (warp == 0) TRACE(8, idx);
       // ---- dS^T = P^T * (dP^T * scale - delta_q * scale): the bracket in fp32, the product as one bf16x2 multiply per pair
       auto dsmul = [&](const uint32_t (&d)[32], int hh) {
-        if (inside) {  // straight-line: the eight metadata loads are issued back to back
+        if (inside || normal) {  // every row uses the plain scale; straight-line: the eight metadata loads go back to back
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 nd = lds_f4(m_nd + hh * 32 + 4 * c4);

@@ -20,6 +20,19 @@ __device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2 (exp2f adds 
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5, far below the bf16 rounding the result gets), exponent patched in with one integer
+// multiply-add. The attention kernels are bound by the 16 ex2 / clk / SM of the MUFU, so a fraction of the exponentials
+// is evaluated this way (the FlashAttention-4 trick). x is clamped to >= -126 (masked scores are -inf).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;       // 1.5 * 2^23: round(x) lands in the low mantissa bits of t
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.055171649903059006f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {  // 16-byte chunk in a [rows][128 B] SW128 tile
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
