@@ -113,9 +113,9 @@ class _Geom:
     """Shapes + key-range tables of one forward (device tensors, no host syncs)."""
     __slots__ = ("B", "N", "M", "H", "D", "enc_lo", "enc_hi", "dec_lo", "dec_hi", "x_lo", "x_hi", "eps", "m_enc", "m_dec", "m_x")
 
-    def build_meta(self, dev):
+    def build_meta(self, dev, encoder: bool = True):
         """Range metadata per attention kind, once per forward (shared by all layers, heads, fwd and bwd)."""
-        if self.N > 0:
+        if self.N > 0 and encoder:
             self.m_enc = ops.attn_ranges(self.B, self.N, self.N, self.enc_lo, self.enc_hi, device=dev)
         if self.M > 0:
             self.m_dec = ops.attn_ranges(self.B, self.M, self.M, self.dec_lo, self.dec_hi, device=dev)
@@ -574,13 +574,20 @@ class EgoM2P(nn.Module):
         g = self._geom(B, N, M)
         g.x_lo, g.x_hi = self._prefix_ranges(encoder_mask, B, M, N, y.device) if N > 0 else (None, None)
         g.dec_lo, g.dec_hi = self._prefix_ranges(decoder_attention_mask, B, M, M, y.device)
-        g.N = 0  # no encoder self-attention on this path
-        g.build_meta(y.device)
-        g.N = N
+        g.build_meta(y.device, encoder=False)  # no encoder self-attention on this path
         h = y.reshape(B * M, D).float().contiguous()
         c = context.reshape(B * N, D).float().contiguous() if N > 0 else torch.zeros(0, D, dtype=f32, device=y.device)
         if N == 0:
-            raise NotImplementedError("decoder with an empty context: use GenerationSampler glue in egom2p_b200.generate")
+            # Unconditional branch of guided ROAR decoding (generate.py:793-802): no context token at all. Softmax over
+            # zero keys times an empty V is exactly 0 and the cross-attention projection has no bias, so every block
+            # reduces to self-attention + MLP. Inference only.
+            if torch.is_grad_enabled() and (y.requires_grad or any(p.requires_grad for p in self.decoder.parameters())):
+                raise NotImplementedError("decoder with an empty context is an inference-only path (wrap it in torch.no_grad())")
+            for i, blk in enumerate(self.decoder):
+                wqkv, wsproj, _, _, _, w13, w2 = self._dec_weights(i)
+                h, _ = _self_attn_fwd(h, blk.norm1.weight, wqkv, wsproj, B, M, g.H, g.m_dec, g.eps)
+                h, _ = _mlp_fwd(h, blk.norm2.weight, w13, w2, g.eps)
+            return self.decoder_norm(h).reshape(B, M, D)
         for i, blk in enumerate(self.decoder):
             h = self._dec_block(i, blk, h, c, g)
         return self.decoder_norm(h).reshape(B, M, D)
