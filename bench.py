@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("EGOM2P_BENCH_BATCH", "16")), help="samples per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("EGOM2P_BENCH_BATCH", "32")), help="samples per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=1)

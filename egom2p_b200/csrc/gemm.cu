@@ -288,32 +288,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else if (EPI == EPI_SWIGLU_BWD) {
         // ---- fc2 dgrad: acc = dg (32 columns per step); with the saved [a | b] group of the same 32 hidden units emit
         // [da | db] (64 bf16 columns, same interleaved layout): da = dg * b * silu'(a), db = dg * silu(a).
-#pragma unroll 1
-        for (int c = 0; c < kHalfCols / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + c * 32, v);
-          tmem_ld_wait();
-          const int cbase = n0 + c * 32;           // hidden-unit base of this step
-          uint32_t da[16], db[16];
+        // The saved [a | b] rows of the NEXT 32 hidden units are fetched (8 x 16 B per row) while the current 32 are
+        // evaluated: the epilogue is otherwise bound by the global-load + TMEM-load round trips, not by its math.
+        constexpr int kSteps = kHalfCols / 32;
+        uint4 abuf[2][8];
+        auto fetch = [&](int c, uint4 (&dst)[8]) {
+          const int cbase = n0 + c * 32;
           if (row_ok && cbase < p.N) {
             const uint4* pab = reinterpret_cast<const uint4*>(p.ab + (int64_t)my_row * p.ld_ab + 2 * cbase);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 ra = pab[j], rb = pab[j + 4];
-              const uint32_t aw[4] = {ra.x, ra.y, ra.z, ra.w}, bw[4] = {rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[u]));
-                const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[u]));
-                const float d0 = __uint_as_float(v[8 * j + 2 * u]), d1 = __uint_as_float(v[8 * j + 2 * u + 1]);
-                const float s0 = 1.f / (1.f + __expf(-fa.x)), s1 = 1.f / (1.f + __expf(-fa.y));
-                da[4 * j + u] = pack_bf16(d0 * fb.x * (s0 * (1.f + fa.x * (1.f - s0))), d1 * fb.y * (s1 * (1.f + fa.y * (1.f - s1))));
-                db[4 * j + u] = pack_bf16(d0 * fa.x * s0, d1 * fa.y * s1);
-              }
-            }
+            for (int j = 0; j < 8; ++j) dst[j] = __ldg(pab + j);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { da[j] = 0u; db[j] = 0u; }
+            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        };
+        fetch(0, abuf[0]);
+#pragma unroll
+        for (int c = 0; c < kSteps; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          if (c + 1 < kSteps) fetch(c + 1, abuf[(c + 1) & 1]);
+          tmem_ld_wait();
+          const int cbase = n0 + c * 32;           // hidden-unit base of this step
+          const uint4(&ab)[8] = abuf[c & 1];
+          uint32_t da[16], db[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 ra = ab[j], rb = ab[j + 4];
+            const uint32_t aw[4] = {ra.x, ra.y, ra.z, ra.w}, bw[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[u]));
+              const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[u]));
+              const float d0 = __uint_as_float(v[8 * j + 2 * u]), d1 = __uint_as_float(v[8 * j + 2 * u + 1]);
+              const float s0 = __fdividef(1.f, 1.f + __expf(-fa.x)), s1 = __fdividef(1.f, 1.f + __expf(-fa.y));
+              da[4 * j + u] = pack_bf16(d0 * fb.x * (s0 * (1.f + fa.x * (1.f - s0))), d1 * fb.y * (s1 * (1.f + fa.y * (1.f - s1))));
+              db[4 * j + u] = pack_bf16(d0 * fa.x * s0, d1 * fa.y * s1);
+            }
           }
           tma_store_wait_read();
           __syncwarp();
