@@ -48,7 +48,8 @@ struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * 4096;  // one 32-row x 128-byte swizzled box per epilogue warp
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // one 32-row x 128-byte swizzled box per epilogue warp (a second
+                                                          // box costs a pipeline stage: measured 9 % slower, tools/bench_gemm_cold.py)
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // + alignment slack
 };
@@ -327,17 +328,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               db[4 * j + u] = pack_bf16(d0 * fa.x * s0, d1 * fa.y * s1);
             }
           }
+          uint8_t* bx = box;
           tma_store_wait_read();
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<uint4*>(box + box_off(lane, j)) = make_uint4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
-            *reinterpret_cast<uint4*>(box + box_off(lane, j + 4)) = make_uint4(db[4 * j], db[4 * j + 1], db[4 * j + 2], db[4 * j + 3]);
+            *reinterpret_cast<uint4*>(bx + box_off(lane, j)) = make_uint4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
+            *reinterpret_cast<uint4*>(bx + box_off(lane, j + 4)) = make_uint4(db[4 * j], db[4 * j + 1], db[4 * j + 2], db[4 * j + 3]);
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && cbase < p.N) {
-            tma_store_2d(&tmCb, box, 2 * cbase, row0);   // output map = dab (rows, 2N) bf16
+          if (lane == 0) {   // (an empty group when the box is out of range keeps the wait_group accounting uniform)
+            if (row0 < p.M && cbase < p.N) tma_store_2d(&tmCb, bx, 2 * cbase, row0);   // output map = dab (rows, 2N) bf16
             tma_store_commit();
           }
         }
@@ -360,6 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v1[j] = __float_as_uint(p1 * gs);
             }
           }
+          uint8_t* bx = box;
           tma_store_wait_read();   // previous store out of this warp's box has been read
           __syncwarp();
 #pragma unroll
@@ -369,26 +372,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk.y = pack_bf16(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
             pk.z = pack_bf16(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
             pk.w = pack_bf16(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
-            *reinterpret_cast<uint4*>(box + box_off(lane, j)) = pk;
+            *reinterpret_cast<uint4*>(bx + box_off(lane, j)) = pk;
             pk.x = pack_bf16(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
             pk.y = pack_bf16(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
             pk.z = pack_bf16(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
             pk.w = pack_bf16(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
-            *reinterpret_cast<uint4*>(box + box_off(lane, j + 4)) = pk;
+            *reinterpret_cast<uint4*>(bx + box_off(lane, j + 4)) = pk;
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && cbase < p.N) {
-            tma_store_2d(&tmCb, box, cbase, row0);
+          if (lane == 0) {
+            if (row0 < p.M && cbase < p.N) tma_store_2d(&tmCb, bx, cbase, row0);
             tma_store_commit();
           }
         }
       } else {
-        // ---- fp32 output (+bias, +residual / accumulate): 32 columns (one 128-byte box row) per step
-#pragma unroll 1
-        for (int c = 0; c < kHalfCols / 32; ++c) {
+        // ---- fp32 output (+bias, +residual / accumulate): 32 columns (one 128-byte box row) per step. The residual row
+        // of the NEXT step is fetched while the current one is written out: the epilogue of the fp32-residual GEMMs (proj,
+        // fc2: 200 MB in + out per launch at b = 16) is bound by these global-load round trips, not by its math.
+        constexpr int kSteps = kHalfCols / 32;
+        const bool use_add = p.addend && splits == 1 && row_ok;
+        float4 abuf[2][8];
+        auto fetch = [&](int c, float4 (&dst)[8]) {
+          const int cbase = n0 + c * 32;
+          const float* arow = p.addend + (int64_t)my_row * p.ld_add + cbase;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = (use_add && cbase + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(arow + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if (p.addend) fetch(0, abuf[0]);
+#pragma unroll
+        for (int c = 0; c < kSteps; ++c) {
           uint32_t v[32];
           tmem_ld32(t_addr + c * 32, v);
+          if (p.addend && c + 1 < kSteps) fetch(c + 1, abuf[(c + 1) & 1]);
           tmem_ld_wait();
           const int cbase = n0 + c * 32;
           if (p.bias) {
@@ -403,29 +420,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          if (p.addend && splits == 1 && row_ok) {
-            const float* arow = p.addend + (int64_t)my_row * p.ld_add + cbase;
+          if (p.addend) {
+            const float4(&av)[8] = abuf[c & 1];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              if (cbase + 4 * j < p.N) {
-                const float4 av = *reinterpret_cast<const float4*>(arow + 4 * j);
-                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + av.x);
-                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + av.y);
-                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + av.z);
-                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + av.w);
-              }
+              v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + av[j].x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + av[j].y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + av[j].z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + av[j].w);
             }
           }
+          uint8_t* bx = box;
           tma_store_wait_read();
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(box + box_off(lane, j)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<uint4*>(bx + box_off(lane, j)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && cbase < p.N) {
-            if (splits > 1) tma_reduce_add_2d(&tmCf, box, cbase, row0);
-            else tma_store_2d(&tmCf, box, cbase, row0);
+          if (lane == 0) {
+            if (row0 < p.M && cbase < p.N) {
+              if (splits > 1) tma_reduce_add_2d(&tmCf, bx, cbase, row0);
+              else tma_store_2d(&tmCf, bx, cbase, row0);
+            }
             tma_store_commit();
           }
         }
