@@ -84,7 +84,7 @@ template <> struct DyVec<false> {
 };
 
 template <bool kDyBf16, int NV>
-__global__ void __launch_bounds__(128, kDyBf16 ? 5 : 4) ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
+__global__ void __launch_bounds__(128, 4) ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
                                                         const float* __restrict__ w, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, const float* __restrict__ dx_in,
                                                         int64_t rows, int dim, int rows_per_cta, float* __restrict__ dx_out,
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128, kDyBf16 ? 5 : 4) ln_bwd_kernel(const void
   for (int64_t row = r0 + warp; row < r1; row += 4) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
-    float4 xv[NV];
+    float4 xv[NV], rv[NV];  // the residual-gradient row is fetched with the other two: one memory round trip per row
     DyVec<kDyBf16> dvr[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(128, kDyBf16 ? 5 : 4) ln_bwd_kernel(const void
       if (i < D4) {
         xv[j] = xr[i];
         dvr[j].load(dy_, row * D4 + i);
+        rv[j] = dx_in ? reinterpret_cast<const float4*>(dx_in + row * dim)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -143,10 +144,7 @@ __global__ void __launch_bounds__(128, kDyBf16 ? 5 : 4) ln_bwd_kernel(const void
         o.y = rs * (d.y * wv.y - m1 - hy * m2);
         o.z = rs * (d.z * wv.z - m1 - hz * m2);
         o.w = rs * (d.w * wv.w - m1 - hw * m2);
-        if (dx_in) {
-          const float4 r = reinterpret_cast<const float4*>(dx_in + row * dim)[i];
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        o.x += rv[j].x; o.y += rv[j].y; o.z += rv[j].z; o.w += rv[j].w;
         reinterpret_cast<float4*>(dx_out + row * dim)[i] = o;
         if (dx_bf16) {
           uint2 pk;
