@@ -563,10 +563,19 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   const int k_blocks = (p.K + BK - 1) / BK;
   // split-K: only for fp32 accumulate/plain outputs, when the output tiles cannot fill the machine and K is long
   int splits = 1;
-  if (EPI == EPI_STORE && !c_bf16 && !p.bias && (!p.addend || p.addend == c_f32) && tiles < sms && k_blocks >= 16) {
-    splits = (2 * sms + tiles - 1) / tiles;
-    splits = splits < k_blocks / 8 ? splits : k_blocks / 8;
-    if (splits < 1) splits = 1;
+  // work units the persistent workers share: output tiles, or 256-row tile pairs; workers: CTAs, or CTA pairs
+  const int units = PAIR ? (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN) : tiles;
+  const int workers = PAIR ? sms / 2 : sms;
+  if (EPI == EPI_STORE && !c_bf16 && !p.bias && (!p.addend || p.addend == c_f32) && units < workers && k_blocks >= 16) {
+    // the number of splits that fills r whole rounds of workers best (r = 1..4; ties: fewer rounds = fewer reduce-adds)
+    float best = 0.f;
+    for (int r = 1; r <= 4; ++r) {
+      int sp = workers * r / units;
+      sp = sp < k_blocks / 8 ? sp : k_blocks / 8;
+      if (sp < 1) sp = 1;
+      const float util = (float)(units * sp) / (float)(((units * sp + workers - 1) / workers) * workers);
+      if (util > best + 0.02f) { best = util; splits = sp; }
+    }
     const int kb_per = (k_blocks + splits - 1) / splits;
     splits = (k_blocks + kb_per - 1) / kb_per;  // no empty splits
   }
