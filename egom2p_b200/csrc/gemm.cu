@@ -1,8 +1,11 @@
-// bf16 GEMM on the 5th-gen tensor cores: tcgen05.mma (cta_group::1, 128 x BN x 16) with fp32 accumulators in TMEM,
-// operands staged by TMA (128B swizzle) through an mbarrier ring, persistent over (tile, k-split) work items with a
-// double-buffered accumulator so the epilogue of item i overlaps the main loop of item i+1.
+// bf16 GEMM on the 5th-gen tensor cores: CTA pairs (cluster 2x1x1) issuing tcgen05.mma.cta_group::2 -- a 256 x BN x 16
+// MMA over the two SMs, each CTA staging its own 128 rows of A and half of the B panel -- with fp32 accumulators in each
+// CTA's TMEM, operands staged by TMA (128B swizzle) through an mbarrier ring, persistent over (tile pair, k-split) work
+// items with a double-buffered accumulator so the epilogue of item i overlaps the main loop of item i+1. The leader CTA
+// (rank 0) issues the MMAs and owns the full / accumulator-free barriers (both producers and both CTAs' epilogue warps
+// arrive on them, the peer through shared::cluster addresses); its commits are multicast to both CTAs.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
+// Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader) + TMEM owner, warps 2..9 = epilogue
 // (two warps per TMEM lane quarter, each owning half of the tile's columns): TMEM -> registers -> (+bias, +residual,
 // or the cross-entropy transforms) -> swizzled smem box -> TMA store. Split-K work items (wgrad: few output tiles,
 // very long K) accumulate with TMA reduce-add, so there are no per-thread atomics and no bounds code.
@@ -10,8 +13,6 @@
 // Operand majors (see include/egom2p_b200.h): K-major tiles are [rows][64 k] (one TMA box); MN-major tiles are
 // [64 k][64 mn] boxes, one per 64 rows of the tile, consumed through MN-major UMMA descriptors -- this is what lets
 // dgrad (B = W stored [N][K]) and wgrad (A = dY^T, B = X^T) run without any transposed copies.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace egom2p {
@@ -615,12 +616,7 @@ static int dispatch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int6
   const int sms = 148;
   const int64_t tiles256 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + 255) / 256);
   const bool use256 = (EPI != EPI_STORE) || (p.N >= 256 && (tiles256 >= 2 * sms || !c_bf16));
-  static const bool pair_ok = getenv("EGOM2P_GEMM_NO_PAIR") == nullptr;
-#define EGO_GEMM_CASE(BN_, AM, BMJ)                                                                              \
-  do {                                                                                                           \
-    if (pair_ok) return launch_gemm<BN_, AM, BMJ, EPI, true>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream);     \
-    return launch_gemm<BN_, AM, BMJ, EPI, false>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream);                 \
-  } while (0)
+#define EGO_GEMM_CASE(BN_, AM, BMJ) return launch_gemm<BN_, AM, BMJ, EPI, true>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream)
   if constexpr (EPI == EPI_SWIGLU_BWD) {  // dg = dY W2 (B consumed MN-major)
     EGO_GEMM_CASE(256, false, true);
   } else if constexpr (EPI != EPI_STORE) {  // CE / SwiGLU-forward epilogues: K-major x K-major
