@@ -62,6 +62,13 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // + alignment slack
 };
 
+// logistic function with ONE MUFU op (tanh.approx, max relative error ~2^-11 -- below the bf16 rounding of every value it
+// feeds) instead of ex2 + rcp: the SwiGLU epilogues evaluate it for every accumulator element
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ uint32_t box_off(int row, int chunk) {  // 16-byte chunk inside a [32][128 B] SW128 box
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
@@ -291,8 +298,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
-              const float g0 = a0 / (1.f + __expf(-a0)) * __uint_as_float(v1[2 * j]);
-              const float g1 = a1 / (1.f + __expf(-a1)) * __uint_as_float(v1[2 * j + 1]);
+              const float g0 = a0 * sigmoid_fast(a0) * __uint_as_float(v1[2 * j]);
+              const float g1 = a1 * sigmoid_fast(a1) * __uint_as_float(v1[2 * j + 1]);
               gp[hh * 16 + j] = pack_bf16(g0, g1);
             }
             tma_store_wait_read();
@@ -334,19 +341,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else if (EPI == EPI_SWIGLU_BWD) {
         // ---- fc2 dgrad: acc = dg (32 columns per step); with the saved [a | b] group of the same 32 hidden units emit
         // [da | db] (64 bf16 columns, same interleaved layout): da = dg * b * silu'(a), db = dg * silu(a).
-        // The saved [a | b] rows of the NEXT 32 hidden units are fetched (8 x 16 B per row) while the current 32 are
-        // evaluated: the epilogue is otherwise bound by the global-load + TMEM-load round trips, not by its math.
+        // The saved [a | b] rows of the NEXT 32 hidden units are fetched while the current 32 are evaluated, and they are
+        // fetched COALESCED (8 lanes per 128-byte row, 4 rows per instruction) and transposed through the warp's staging box:
+        // one 16-byte load per lane and row otherwise costs 32 cache lines per instruction and the LSU, not the tensor pipe,
+        // bounds the kernel (178 us against 93 us for the same GEMM with a plain epilogue).
         constexpr int kSteps = kHalfCols / 32;
         uint4 abuf[2][8];
         auto fetch = [&](int c, uint4 (&dst)[8]) {
           const int cbase = n0 + c * 32;
-          if (row_ok && cbase < p.N) {
-            const uint4* pab = reinterpret_cast<const uint4*>(p.ab + (int64_t)my_row * p.ld_ab + 2 * cbase);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = __ldg(pab + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+          for (int i = 0; i < 8; ++i) {
+            const int r = row0 + 4 * i + (lane >> 3);
+            dst[i] = (r < p.M && cbase < p.N)
+                         ? __ldg(reinterpret_cast<const uint4*>(p.ab + (int64_t)r * p.ld_ab + 2 * cbase) + (lane & 7))
+                         : make_uint4(0u, 0u, 0u, 0u);
           }
         };
         fetch(0, abuf[0]);
@@ -355,9 +363,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t v[32];
           tmem_ld32(t_addr + c * 32, v);
           if (c + 1 < kSteps) fetch(c + 1, abuf[(c + 1) & 1]);
-          tmem_ld_wait();
           const int cbase = n0 + c * 32;           // hidden-unit base of this step
-          const uint4(&ab)[8] = abuf[c & 1];
+          uint4 ab[8];
+          tma_store_wait_read();   // the previous store out of this warp's box has been read
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(box + box_off(4 * i + (lane >> 3), lane & 7)) = abuf[c & 1][i];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ab[j] = *reinterpret_cast<const uint4*>(box + box_off(lane, j));  // this lane's row
+          __syncwarp();            // every lane holds its row before the box is reused for the outputs
+          tmem_ld_wait();
           uint32_t da[16], db[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -368,14 +384,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[u]));
               const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[u]));
               const float d0 = __uint_as_float(v[8 * j + 2 * u]), d1 = __uint_as_float(v[8 * j + 2 * u + 1]);
-              const float s0 = __fdividef(1.f, 1.f + __expf(-fa.x)), s1 = __fdividef(1.f, 1.f + __expf(-fa.y));
+              const float s0 = sigmoid_fast(fa.x), s1 = sigmoid_fast(fa.y);
               da[4 * j + u] = pack_bf16(d0 * fb.x * (s0 * (1.f + fa.x * (1.f - s0))), d1 * fb.y * (s1 * (1.f + fa.y * (1.f - s1))));
               db[4 * j + u] = pack_bf16(d0 * fa.x * s0, d1 * fa.y * s1);
             }
           }
           uint8_t* bx = box;
-          tma_store_wait_read();
-          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             *reinterpret_cast<uint4*>(bx + box_off(lane, j)) = make_uint4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
