@@ -39,23 +39,22 @@ struct GemmParams {
   // SwiGLU epilogues: ab = [a | b] interleaved in groups of 32 columns (bf16), row pitch ld_ab
   const uint16_t* ab;
   int64_t ld_ab;
-  int cluster;  // 1: launched as CTA pairs (cluster 2x1x1) that share the B panel of their two M tiles through TMA multicast
   int v0;
   float* part_max;
   float* part_sum;
   float* tgt_logit;
 };
 
-// PAIR: the kernel runs as CTA pairs (cluster 2x1x1) issuing tcgen05.mma.cta_group::2 -- a 256 x BN tile per pair, each CTA
+// The kernel runs as CTA pairs (cluster 2x1x1) issuing tcgen05.mma.cta_group::2 -- a 256 x BN tile per pair, each CTA
 // staging its own 128 rows of A and HALF of the B panel. A single-CTA 128 x 256 tile moves 12 KB of operands through shared
 // memory per 128-cycle MMA while TMA refills the same 12 KB: ~188 B/clk against the 128 B/clk an SM's shared memory delivers,
 // i.e. the tensor pipe idles a third of the time (ncu: 66 % active). The pair halves the B traffic per SM and deepens the ring.
-template <int BN, bool PAIR>
+template <int BN>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
+  static constexpr int kBBytes = (BN / 2) * BK * 2;  // this CTA's half of the B panel
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = PAIR ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : 6);
+  static constexpr int kStages = BN == 256 ? 6 : 8;
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // one 32-row x 128-byte swizzled box per epilogue warp (a second
                                                           // box costs a pipeline stage: measured 9 % slower, tools/bench_gemm_cold.py)
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
@@ -73,11 +72,11 @@ __device__ __forceinline__ uint32_t box_off(int row, int chunk) {  // 16-byte ch
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmCb, const __grid_constant__ CUtensorMap tmCf, const GemmParams p) {
-  using S = GemmSmem<BN, PAIR>;
+  using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -98,8 +97,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // Pair mode: the two CTAs of a pair walk the same work items; rank r owns M tile 2 * pair + r (its 128 rows of A and of
   // the accumulator) and stages the rows [n0 + r * BN/2, +BN/2) of B. A pair past the last M tile still takes part in the
   // loads; its TMA reads are zero-filled and its stores are clipped.
-  constexpr int cl = PAIR ? 2 : 1;
-  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  constexpr int cl = 2;
+  const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
   const int worker = blockIdx.x / cl, n_workers = gridDim.x / cl;
   const int total_items = ((m_tiles + cl - 1) / cl) * n_tiles * splits;
@@ -118,12 +117,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_mbar_init();
   }
   if (warp == 1) {
-    if (PAIR) tmem_alloc_pair<2 * BN>(tmem_slot);
-    else tmem_alloc<2 * BN>(tmem_slot);
+    tmem_alloc_pair<2 * BN>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync();  // the peer's mbarriers are initialised before anything signals them
+  cluster_sync();  // the peer's mbarriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -141,37 +139,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* a = sA + stage * S::kABytes;
         uint8_t* b = sB + stage * S::kBBytes;
-        if (PAIR) {
-          if (elect_one()) {  // bytes and completions are credited to the leader's barrier (the one its MMA warp waits on)
-            if (leader) mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-            else mbar_expect_tx_cluster(cluster_map(&full_bar[stage], 0), S::kStageBytes);
-            if (!A_MN) {
-              tma_load_2d_pair(a, &tmA, &full_bar[stage], k0, m0);
-            } else {
-#pragma unroll
-              for (int h = 0; h < BM / 64; ++h) tma_load_2d_pair(a + h * 8192, &tmA, &full_bar[stage], m0 + h * 64, k0);
-            }
-            if (!B_MN) {
-              tma_load_2d_pair(b, &tmB, &full_bar[stage], k0, n0 + (int)crank * (BN / 2));
-            } else {
-#pragma unroll
-              for (int h = 0; h < BN / 128; ++h)
-                tma_load_2d_pair(b + h * 8192, &tmB, &full_bar[stage], n0 + ((int)crank * (BN / 128) + h) * 64, k0);
-            }
-          }
-        } else if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+        if (elect_one()) {  // bytes and completions are credited to the leader's barrier (the one its MMA warp waits on)
+          if (leader) mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          else mbar_expect_tx_cluster(cluster_map(&full_bar[stage], 0), S::kStageBytes);
           if (!A_MN) {
-            tma_load_2d(a, &tmA, &full_bar[stage], k0, m0);
+            tma_load_2d_pair(a, &tmA, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
-            for (int h = 0; h < BM / 64; ++h) tma_load_2d(a + h * 8192, &tmA, &full_bar[stage], m0 + h * 64, k0);
+            for (int h = 0; h < BM / 64; ++h) tma_load_2d_pair(a + h * 8192, &tmA, &full_bar[stage], m0 + h * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d(b, &tmB, &full_bar[stage], k0, n0);
+            tma_load_2d_pair(b, &tmB, &full_bar[stage], k0, n0 + (int)crank * (BN / 2));
           } else {
 #pragma unroll
-            for (int h = 0; h < BN / 64; ++h) tma_load_2d(b + h * 8192, &tmB, &full_bar[stage], n0 + h * 64, k0);
+            for (int h = 0; h < BN / 128; ++h)
+              tma_load_2d_pair(b + h * 8192, &tmB, &full_bar[stage], n0 + ((int)crank * (BN / 128) + h) * 64, k0);
           }
         }
         __syncwarp();
@@ -182,7 +164,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ MMA issuer
     // Warp-uniform loop; descriptors are built once per stage in uniform registers and advanced by a constant per
     // k-step, so each tcgen05.mma costs a couple of instructions to issue (the tensor pipe needs one every 128 cycles).
-    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);  // M = 256 over the pair
     constexpr uint64_t kStepA = A_MN ? (2048 >> 4) : (32 >> 4), kStepB = B_MN ? (2048 >> 4) : (32 >> 4);
     int stage = 0;
     uint32_t phase = 0;
@@ -203,19 +185,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint64_t da0 = A_MN ? umma_desc_mnmajor_sw128(a_addr, 8192) : umma_desc_kmajor_sw128(a_addr);
         const uint64_t db0 = B_MN ? umma_desc_mnmajor_sw128(b_addr, 8192) : umma_desc_kmajor_sw128(b_addr);
         if (elect_one()) {
-          if (PAIR) {
-            umma_bf16_ss_pair(d_tmem, da0, db0, idesc, kb > kb0 ? 1u : 0u);
+          umma_bf16_ss_pair(d_tmem, da0, db0, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BK / 16; ++k) umma_bf16_ss_pair(d_tmem, da0 + k * kStepA, db0 + k * kStepB, idesc, 1u);
-            umma_commit_pair(&empty_bar[stage]);                    // frees the stage in both CTAs
-            if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);   // accumulator halves ready in both CTAs
-          } else {
-            umma_bf16_ss(d_tmem, da0, db0, idesc, kb > kb0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 1; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da0 + k * kStepA, db0 + k * kStepB, idesc, 1u);
-            umma_commit(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
-          }
+          for (int k = 1; k < BK / 16; ++k) umma_bf16_ss_pair(d_tmem, da0 + k * kStepA, db0 + k * kStepB, idesc, 1u);
+          umma_commit_pair(&empty_bar[stage]);                    // frees the stage in both CTAs
+          if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);   // accumulator halves ready in both CTAs
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -509,7 +483,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (!PAIR || leader) mbar_arrive(&tempty_bar[acc]);
+        if (leader) mbar_arrive(&tempty_bar[acc]);
         else mbar_arrive_cluster(cluster_map(&tempty_bar[acc], 0));
       }
     }
@@ -518,11 +492,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync();  // no CTA leaves while its peer may still signal its mbarriers / read its smem
+  cluster_sync();  // no CTA leaves while its peer may still signal its mbarriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    if (PAIR) tmem_dealloc_pair<2 * BN>(tmem_base);
-    else tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc_pair<2 * BN>(tmem_base);
   }
 }
 
@@ -537,17 +510,16 @@ static int sm_count() {
   return cached;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_t ldb, uint16_t* c_bf16, float* c_f32,
                        int64_t ldc, GemmParams p, cudaStream_t stream) {
-  using S = GemmSmem<BN, PAIR>;
+  using S = GemmSmem<BN>;
   CUtensorMap tmA, tmB, tmCb, tmCf;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&tmA, A, p.M, p.K, lda, BM, BK);
   else       rc = make_tmap_bf16_2d(&tmA, A, p.K, p.M, lda, BK, 64);
   if (rc) return rc;
-  p.cluster = PAIR ? 1 : 0;
-  if (!B_MN) rc = make_tmap_bf16_2d(&tmB, B, p.N, p.K, ldb, PAIR ? BN / 2 : BN, BK);
+  if (!B_MN) rc = make_tmap_bf16_2d(&tmB, B, p.N, p.K, ldb, BN / 2, BK);
   else       rc = make_tmap_bf16_2d(&tmB, B, p.K, p.N, ldb, BK, 64);
   if (rc) return rc;
   tmCb = tmA;
@@ -563,7 +535,7 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   }
   p.out_bf16 = c_bf16 != nullptr;
   p.out_f32 = c_f32 != nullptr;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, PAIR>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -574,13 +546,12 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
     attr_set = true;
   }
   const int sms = sm_count();
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int k_blocks = (p.K + BK - 1) / BK;
   // split-K: only for fp32 accumulate/plain outputs, when the output tiles cannot fill the machine and K is long
   int splits = 1;
-  // work units the persistent workers share: output tiles, or 256-row tile pairs; workers: CTAs, or CTA pairs
-  const int units = PAIR ? (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN) : tiles;
-  const int workers = PAIR ? sms / 2 : sms;
+  // work units the persistent workers (CTA pairs) share: 256-row tile pairs
+  const int units = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN);
+  const int workers = sms / 2;
   if (EPI == EPI_STORE && !c_bf16 && !p.bias && (!p.addend || p.addend == c_f32) && units < workers && k_blocks >= 16) {
     // the number of splits that fills r whole rounds of workers best (r = 1..4; ties: fewer rounds = fewer reduce-adds)
     float best = 0.f;
@@ -598,12 +569,6 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   if (splits > 1 && !p.addend) {  // reduce-add needs a zeroed destination (an aliased addend means "accumulate into C")
     cudaError_t e = cudaMemset2DAsync(c_f32, ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), p.M, stream);
     if (e != cudaSuccess) { set_error("gemm: memset: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
-  }
-  if (!PAIR) {
-    const int items = tiles * splits;
-    const int grid = items < sms ? items : sms;
-    kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmCb, tmCf, p);
-    return check_launch("gemm_bf16");
   }
   // CTA pairs: clusters of 2 along x
   const int pair_items = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN) * splits;
@@ -630,7 +595,7 @@ static int dispatch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int6
   const int sms = 148;
   const int64_t tiles256 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + 255) / 256);
   const bool use256 = (EPI != EPI_STORE) || (p.N >= 256 && (tiles256 >= 2 * sms || !c_bf16));
-#define EGO_GEMM_CASE(BN_, AM, BMJ) return launch_gemm<BN_, AM, BMJ, EPI, true>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream)
+#define EGO_GEMM_CASE(BN_, AM, BMJ) return launch_gemm<BN_, AM, BMJ, EPI>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream)
   if constexpr (EPI == EPI_SWIGLU_BWD) {  // dg = dY W2 (B consumed MN-major)
     EGO_GEMM_CASE(256, false, true);
   } else if constexpr (EPI != EPI_STORE) {  // CE / SwiGLU-forward epilogues: K-major x K-major
