@@ -64,6 +64,57 @@ def make_batch(b: int, seed: int, pin: bool):
     return md
 
 
+def load_ref_masks():
+    """Masks drawn by the reference's UnifiedMasking (oracle/gen_golden_masks.py): the ragged 'reference-distribution' regime."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_masks_egob.npz"))
+    return g
+
+
+def make_batch_ref_masks(b: int, offset: int, seed: int, pin: bool, g=None):
+    from egom2p_b200.modality_info import MODALITY_INFO as MI
+    g = load_ref_masks() if g is None else g
+    rng = np.random.default_rng(seed)
+    n = int(g["n"])
+    sel = [(offset + i) % n for i in range(b)]
+    md = {}
+    for m in sorted(MI):
+        L, V = MI[m]["max_tokens"], MI[m]["vocab_size"]
+        t = torch.from_numpy(rng.integers(0, V, size=(b, L), dtype=np.int64))
+        if L == 5120:
+            t = t.reshape(b, 5, 32, 32)
+        imask = np.stack([np.unpackbits(g[m + "_input_mask"][i])[:L].astype(bool) for i in sel])
+        tmask = np.stack([np.unpackbits(g[m + "_target_mask"][i])[:L].astype(bool) for i in sel])
+        cnt = np.stack([g[m + "_attn"][i] for i in sel]).astype(np.int32)
+        d = {"tensor": t, "input_mask": torch.from_numpy(imask), "target_mask": torch.from_numpy(tmask),
+             "decoder_attention_mask": torch.from_numpy(cnt)}
+        md[m] = {k: (v.pin_memory() if pin else v) for k, v in d.items()}
+    return md
+
+
+def step_flops(md) -> float:
+    """Mask-aware algorithmic FLOPs of one training step on this batch (3 x forward)."""
+    from egom2p_b200.modality_info import MODALITY_INFO as MI
+    D, F, Le, Ld, N, M = 768, 2048, 12, 12, N_ENC, N_DEC
+    mods = sorted(MI)
+    b = md[mods[0]]["input_mask"].shape[0]
+    total = 0.0
+    for i in range(b):
+        n_in = {m: int((~md[m]["input_mask"][i]).sum()) for m in mods}
+        n_tg = {m: int((~md[m]["target_mask"][i]).sum()) for m in mods}
+        n_enc = min(sum(n_in.values()), N)
+        # targets are kept in modality order up to the budget
+        left, kept = M, {}
+        for m in mods:
+            kept[m] = min(n_tg[m], left)
+            left -= kept[m]
+        enc = Le * (N * (4 * D * D + 3 * D * F) + 2 * N * n_enc * D)
+        ctx = N * D * D
+        dec = Ld * (M * (6 * D * D + 3 * D * F) + 2 * N * D * D + 2 * sum(v * v for v in kept.values()) * D + 2 * M * n_enc * D)
+        head = sum(kept[m] * D * MI[m]["vocab_size"] for m in mods)
+        total += 3 * 2.0 * (enc + ctx + dec + head)
+    return total
+
+
 def md_bytes(md):
     return int(sum(v.numel() * v.element_size() for d in md.values() for v in d.values()))
 
@@ -173,6 +224,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=int(os.environ.get("EGOM2P_BENCH_BATCH", "32")), help="samples per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--regime", default="dense", choices=["dense", "reference-masks"],
+                    help="dense: SURVEY 8(d) headline synthetic regime; reference-masks: ragged masks drawn by the reference's UnifiedMasking")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=1)
     args = ap.parse_args()
@@ -203,7 +256,13 @@ def main():
                             lr=1e-4, betas=(0.9, 0.95), eps=1e-8, fused=True)
     params = list(model.parameters())
 
-    host_batches = [make_batch(b, 1234 + rank * 1000 + s, pin=True) for s in range(2)]
+    if args.regime == "dense":
+        host_batches = [make_batch(b, 1234 + rank * 1000 + s, pin=True) for s in range(2)]
+        flops_per_step = b * FLOP_PER_SAMPLE_STEP
+    else:
+        gm = load_ref_masks()
+        host_batches = [make_batch_ref_masks(b, (rank * 2 + s) * b, 1234 + rank * 1000 + s, pin=True, g=gm) for s in range(2)]
+        flops_per_step = float(np.mean([step_flops(hb) for hb in host_batches]))
     dev_batches = [{m: {k: v.to(dev) for k, v in d.items()} for m, d in hb.items()} for hb in host_batches]
 
     def step(md):
@@ -263,7 +322,7 @@ def main():
         value = gbatch * NOMINAL_TOKENS / t_step
         e2e_val = gbatch * NOMINAL_TOKENS / (ms_e2e / args.steps / 1e3)
         hbm, tf_burst, tf_sus, src = peaks()
-        tflops = gbatch * FLOP_PER_SAMPLE_STEP / t_step / 1e12 / world  # per GPU
+        tflops = flops_per_step / t_step / 1e12  # per GPU (rank 0's batches; mask-aware FLOPs in the ragged regime)
         g = fam.get("gemm", {"ms": 1e-9, "work": 0.0, "launches": 1})
         achieved = g["work"] / (g["ms"] / 1e3) / 1e12
         total_kernel_ms = sum(d["ms"] for d in fam.values())
@@ -272,8 +331,12 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "ego-b mod4 (egom2p_base_12e_12d_swiglu_nobias, 396.2M params) training step: fwd + bwd + "
-                                   "clip_grad_norm(1.0) + AdamW; dense synthetic regime, 2048 encoder + 2048 decoder tokens/sample "
-                                   "(1009 rgb + 1009 depth + 15 cam + 15 gaze per side), random-init weights",
+                                   "clip_grad_norm(1.0) + AdamW; " +
+                                   ("dense synthetic regime, 2048 encoder + 2048 decoder tokens/sample "
+                                    "(1009 rgb + 1009 depth + 15 cam + 15 gaze per side)" if args.regime == "dense" else
+                                    "reference-distribution regime: masks drawn by the reference UnifiedMasking (budgets 2048 / 2048, "
+                                    "ragged: mean 1086 valid inputs / 891 valid targets), mask-aware FLOPs") + ", random-init weights",
+                       "regime": args.regime,
                        "global_batch": gbatch, "batch_per_gpu": b, "parallelism": f"dp{world}", "nominal_tokens_per_sample": NOMINAL_TOKENS,
                        "l2_policy": "working set (activations + 1.6 GB weights) far exceeds the 126 MB L2; no explicit flush",
                        "model_tflops_per_gpu": tflops, "mfu_vs_2250_spec": tflops / 2250.0,
