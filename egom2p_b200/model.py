@@ -126,6 +126,12 @@ def _zeros(n, dev):
     return torch.zeros(n, dtype=f32, device=dev)
 
 
+# Bumped by every backward of the block / context / head functions below. The bf16 operand cache of EgoM2P is keyed on it:
+# weights whose gradients were just produced are about to be rewritten by an optimizer, and the fused CUDA optimizers
+# (torch._fused_adamw_) do not bump Tensor._version, so the version counter alone would leave the cache stale.
+_GRAD_GEN = [0]
+
+
 def _split_w13_grad(dw13, F):
     """dw13 rows are interleaved [32 x fc1 | 32 x fc3] groups (see EgoM2P._bf16_w13): back to (fc1.grad, fc3.grad)."""
     Fp, D = dw13.shape[0] // 2, dw13.shape[1]
@@ -191,6 +197,7 @@ class _EncoderBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dx2):
+        _GRAD_GEN[0] += 1
         x, n1w, n2w, x1, *rest = ctx.saved_tensors
         sa, sm = rest[:6], rest[6:]
         wqkv, wproj, w13, w2 = ctx.wb
@@ -226,6 +233,7 @@ class _DecoderBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy3):
+        _GRAD_GEN[0] += 1
         (y, context, n1w, qnw, cnw, n2w, y1, y2, meanq, rstdq, hq, q, meanc, rstdc, hc, kv, o2, lse2, *rest) = ctx.saved_tensors
         sa, sm = rest[:6], rest[6:]
         wqkv, wsproj, wq, wkv, wxproj, w13, w2 = ctx.wb
@@ -266,6 +274,7 @@ class _ContextFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dctx):
+        _GRAD_GEN[0] += 1
         x, norm_w, mean, rstd, h = ctx.saved_tensors
         dctx = dctx.contiguous()
         dcb = ops.cast_bf16(dctx)
@@ -345,6 +354,7 @@ class _HeadLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *dlosses):
+        _GRAD_GEN[0] += 1
         y, norm_w, mean, rstd = ctx.saved_tensors
         dev = y.device
         D = y.shape[1]
@@ -490,7 +500,7 @@ class EgoM2P(nn.Module):
 
     # ------------------------------------------------------------------ bf16 operand cache (refreshed when a master changes)
     def _bf16(self, key, *params: torch.Tensor, pad32: bool = False) -> torch.Tensor:
-        ver = tuple((p.data_ptr(), p._version) for p in params)
+        ver = (_GRAD_GEN[0],) + tuple((p.data_ptr(), p._version) for p in params)
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
@@ -516,6 +526,11 @@ class EgoM2P(nn.Module):
                 v[:, i].copy_(tmp.view(Fp // 32, 32, D))
         self._wcache[key] = (ver, wb)
         return wb
+
+    def invalidate_weight_cache(self):
+        """Force a re-cast of every bf16 operand at the next forward. Needed only after an in-place weight update that
+        neither bumps Tensor._version nor follows a backward of this module (see _GRAD_GEN)."""
+        _GRAD_GEN[0] += 1
 
     def _enc_weights(self, i: int):
         b = self.encoder[i]

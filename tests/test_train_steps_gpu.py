@@ -1,0 +1,84 @@
+"""GPU: several optimizer steps of the training loop body (forward + backward + clip_grad_norm_(1.0) + fused AdamW,
+run_training_egom2p.py:701-746) against the same loop over the CPU oracle. Guards the bf16 operand cache of the module:
+every step must run on the weights the optimizer just wrote, so the loss trajectory has to follow the oracle's
+(a stale cache shows up from step 2 on; the learning rate is large so that one update moves the loss visibly)."""
+import random
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import egom2p_oracle as orc  # noqa: E402
+import synth  # noqa: E402
+from test_model_gpu import build_model, to_cuda  # noqa: E402
+
+STEPS = 4
+LR = 3e-3
+
+
+def _oracle_losses(sd, cfg, md, n_enc, n_dec, orders):
+    leaf = {}
+    for k, v in sd.items():
+        if k.endswith("to_logits.weight") or (k.startswith("decoder_embeddings") and k.endswith("mod_emb")):
+            continue
+        leaf[k] = v.clone().requires_grad_(v.is_floating_point() and not k.endswith("pos_emb")
+                                           and not (k.endswith(".bias") and "proj_context" not in k))
+    for m in cfg["mods"]:
+        leaf[f"decoder_embeddings.{m}.to_logits.weight"] = leaf[f"decoder_embeddings.{m}.token_emb.weight"]
+        leaf[f"decoder_embeddings.{m}.mod_emb"] = leaf[f"encoder_embeddings.{m}.mod_emb"]
+    params = list({id(t): t for t in leaf.values() if t.requires_grad}.values())
+    opt = torch.optim.AdamW(params, lr=LR, betas=(0.9, 0.95), weight_decay=0.05)
+    losses = []
+    for order in orders:
+        out = orc.forward(leaf, cfg, md, n_enc, n_dec, dec_order=order, loss_type="mod")
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(out["loss"].item())
+    return losses
+
+
+def test_loss_trajectory_follows_oracle():
+    cfg = synth.make_cfg(192, 3, 2, 2, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"], video_vocab=512, video_thw=(5, 4, 4))
+    md = synth.make_batch(cfg, B=4, seed=11,
+                          n_in={"tok_cam": [5, 0, 30, 2], "tok_depth": [30, 10, 0, 1], "tok_gaze": [4, 0, 30, 0], "tok_rgb": [25, 40, 4, 0]},
+                          n_tgt={"tok_cam": [10, 30, 0, 1], "tok_depth": [20, 0, 40, 0], "tok_gaze": [3, 0, 0, 0], "tok_rgb": [15, 18, 70, 0]})
+    sd = synth.make_state_dict(cfg, 5)
+    mods = list(cfg["mods"])
+    orders = []
+    for s in range(STEPS):
+        random.seed(100 + s)
+        orders.append(random.sample(mods, len(mods)))
+    ref = _oracle_losses(sd, cfg, md, 64, 48, orders)
+
+    model = build_model(cfg).cuda()
+    model.load_state_dict(sd, strict=True)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=LR, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+    mdc = to_cuda(md)
+    got = []
+    for s in range(STEPS):
+        random.seed(100 + s)
+        loss, _ = model(mdc, 64, 48, loss_type="mod")
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        got.append(loss.item())
+    assert ref[0] - ref[-1] > 0.05 * ref[0], f"oracle loss did not move enough for the test to discriminate: {ref}"
+    for s, (a, b) in enumerate(zip(got, ref)):
+        tol = 1e-3 if s == 0 else 1.5e-2   # later steps compound bf16-vs-fp32 update differences; a stale cache is ~15 % off
+        assert abs(a - b) / abs(b) < tol, f"step {s}: loss {a} vs oracle {b}\nours {got}\noracle {ref}"
+
+    # the cached bf16 operands are exactly the rounded masters after the last update, once the next forward refreshes them
+    with torch.no_grad():
+        random.seed(0)
+        model(mdc, 64, 48, loss_type="mod")
+    blk = model.encoder[0]
+    wq = model._wcache[("e", 0, "qkv")][1]
+    assert torch.equal(wq, blk.attn.qkv.weight.detach().to(torch.bfloat16))
+    w2 = model._wcache[("e", 0, "w2")][1]
+    F = blk.mlp.fc2.weight.shape[1]
+    assert torch.equal(w2[:, :F], blk.mlp.fc2.weight.detach().to(torch.bfloat16))

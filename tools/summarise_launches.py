@@ -15,8 +15,15 @@ for r in rd:
     unit = r.get("Metric Unit", "ns")
     us = v / 1e3 if unit in ("ns", "nsecond") else v if unit in ("us", "usecond") else v * 1e3
     rows.append((r["Kernel Name"], us))
-per = len(rows) // nsteps
-last = rows[-per:]
+# the LAST step = everything after the previous step's optimizer launches (the first step of a process also holds one-off
+# launches -- optimizer-state zero fills, initial weight casts -- so cutting the list into equal parts would mis-attribute them)
+opt = [i for i, (n, _) in enumerate(rows) if "FusedOptimizer" in n or "adamw" in n.lower()]
+ends = [i for i in opt if i + 1 < len(rows) and i + 1 not in set(opt)]
+if ends:
+    last = rows[ends[-1] + 1:]
+else:
+    per = len(rows) // nsteps
+    last = rows[-per:]
 agg = defaultdict(lambda: [0, 0.0])
 for name, us in last:
     m = re.match(r"(?:void )?([\w:]+)", name)
