@@ -89,6 +89,52 @@ __global__ void __launch_bounds__(kEwThreads) cast_kernel(const float* __restric
   }
 }
 
+// One launch that re-casts a whole list of fp32 master weights into their bf16 GEMM operands (the per-step refresh after the
+// optimizer wrote the masters). A block = one chunk of rows of one tensor, found by bisection over the items' first chunks;
+// group > 0 writes the rows into the interleaved [group x fc1 | group x fc3] layout the SwiGLU-epilogue GEMM consumes.
+struct CastItem {
+  const float* src;
+  uint16_t* dst;
+  int64_t rows;
+  int64_t first_chunk;
+  int32_t cols, dst_ld, group, slot, rows_per_chunk, pad_;
+};
+static_assert(sizeof(CastItem) == 56, "CastItem layout is part of the C ABI (egom2p_cast_item)");
+__global__ void __launch_bounds__(kEwThreads) cast_multi_kernel(const CastItem* __restrict__ items, int n_items) {
+  __shared__ CastItem it;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {  // last item with first_chunk <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].first_chunk <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    it = items[lo];
+  }
+  __syncthreads();
+  const int64_t r0 = ((int64_t)blockIdx.x - it.first_chunk) * it.rows_per_chunk;
+  const int nr = (int)min((int64_t)it.rows_per_chunk, it.rows - r0);
+  auto dst_row = [&](int64_t r) -> int64_t {
+    return it.group > 0 ? (r / it.group) * 2 * it.group + (int64_t)it.slot * it.group + r % it.group : r;
+  };
+  if ((it.cols & 3) == 0 && (it.dst_ld & 3) == 0) {
+    const int c4 = it.cols >> 2;
+    for (int i = threadIdx.x; i < nr * c4; i += kEwThreads) {
+      const int rr = i / c4, cc = i - rr * c4;
+      const float4 v = reinterpret_cast<const float4*>(it.src + (r0 + rr) * it.cols)[cc];
+      uint2 pk;
+      pk.x = pack_bf16(v.x, v.y);
+      pk.y = pack_bf16(v.z, v.w);
+      reinterpret_cast<uint2*>(it.dst + dst_row(r0 + rr) * it.dst_ld)[cc] = pk;
+    }
+  } else {
+    for (int i = threadIdx.x; i < nr * it.cols; i += kEwThreads) {
+      const int rr = i / it.cols, cc = i - rr * it.cols;
+      const __nv_bfloat16 h = __float2bfloat16(it.src[(r0 + rr) * it.cols + cc]);
+      it.dst[dst_row(r0 + rr) * it.dst_ld + cc] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kEwThreads) add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
                                                          float* __restrict__ out, uint16_t* __restrict__ outb) {
   const int64_t n4 = n >> 2;
@@ -206,6 +252,12 @@ extern "C" int egom2p_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t 
   EGO_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "cast_f32_to_bf16: misaligned");
   cast_kernel<<<ew_grid(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(src, dst, n);
   return check_launch("cast_f32_to_bf16");
+}
+extern "C" int egom2p_cast_f32_to_bf16_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(items_dev && n_items > 0 && n_chunks > 0 && n_chunks < (int64_t)INT32_MAX, "cast_f32_to_bf16_multi: bad argument");
+  cast_multi_kernel<<<(unsigned)n_chunks, kEwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const CastItem*>(items_dev), n_items);
+  return check_launch("cast_f32_to_bf16_multi");
 }
 extern "C" int egom2p_add_f32(const float* a, const float* b, int64_t n, float* out, uint16_t* out_bf16, void* stream) {
   using namespace egom2p;

@@ -451,7 +451,8 @@ class EgoM2P(nn.Module):
         nn.init.normal_(self.mask_token, std=self.init_std)
         self.register_tokens = None
         self.init_weights()
-        self._wcache: Dict[Any, Tuple[int, torch.Tensor]] = {}
+        self._wcache: Dict[Any, tuple] = {}
+        self._wplan = None
 
     # ------------------------------------------------------------------ construction helpers (reference :179-249)
     def share_modality_embeddings(self):
@@ -500,32 +501,58 @@ class EgoM2P(nn.Module):
 
     # ------------------------------------------------------------------ bf16 operand cache (refreshed when a master changes)
     def _bf16(self, key, *params: torch.Tensor, pad32: bool = False) -> torch.Tensor:
-        ver = (_GRAD_GEN[0],) + tuple((p.data_ptr(), p._version) for p in params)
+        """bf16 GEMM operand of one weight (or of the fc1 | fc3 pair). Entries: (ptrs, versions, generation, operand, params)."""
+        ptrs = tuple(p.data_ptr() for p in params)
+        vers = tuple(p._version for p in params)
         hit = self._wcache.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
+        if hit is not None and hit[0] == ptrs:
+            if hit[1] == vers and hit[2] == _GRAD_GEN[0]:
+                return hit[3]
+            self._refresh_operands()   # some master changed: one launch re-casts every registered operand
+            hit = self._wcache[key]
+            if hit[1] == vers and hit[2] == _GRAD_GEN[0]:
+                return hit[3]
         dev = params[0].device
         if len(params) == 1:
             p = params[0]
             pad = (-p.shape[1]) % (32 if pad32 else 8)
             if pad == 0:
-                out = hit[1] if hit is not None and hit[1].shape == p.shape else None
-                wb = ops.cast_bf16(p.detach(), out)
+                wb = ops.cast_bf16(p.detach())
             else:  # inner dim padded with zero columns so TMA row pitches stay 16-byte multiples (e.g. hidden 682)
-                wb = hit[1] if hit is not None else torch.zeros(p.shape[0], p.shape[1] + pad, dtype=bf16, device=dev)
+                wb = torch.zeros(p.shape[0], p.shape[1] + pad, dtype=bf16, device=dev)
                 wb[:, :p.shape[1]].copy_(ops.cast_bf16(p.detach()))
         else:  # fc1 | fc3 -> one N = 2*hidden GEMM operand with rows interleaved in groups of 32 (hidden padded to 32)
             F, D = params[0].shape
             Fp = (F + 31) // 32 * 32
-            wb = hit[1] if hit is not None else torch.zeros(2 * Fp, D, dtype=bf16, device=dev)
+            wb = torch.zeros(2 * Fp, D, dtype=bf16, device=dev)
             v = wb.view(Fp // 32, 2, 32, D)
             for i, p in enumerate(params):
                 tmp = ops.cast_bf16(p.detach())
                 if Fp != F:
                     tmp = torch.cat([tmp, torch.zeros(Fp - F, D, dtype=bf16, device=dev)], 0)
                 v[:, i].copy_(tmp.view(Fp // 32, 32, D))
-        self._wcache[key] = (ver, wb)
+        self._wcache[key] = (ptrs, vers, _GRAD_GEN[0], wb, params)
+        self._wplan = None
         return wb
+
+    def _refresh_operands(self):
+        """Re-cast every cached operand whose masters still live at the same addresses, in one launch (ops.CastPlan)."""
+        live = {k: e for k, e in self._wcache.items()
+                if e[0] == tuple(p.data_ptr() for p in e[4]) and all(p.dim() == 2 and p.is_contiguous() for p in e[4])}
+        if not live:
+            return
+        sig = tuple((k, e[0], e[3].data_ptr()) for k, e in live.items())
+        if self._wplan is None or self._wplan[0] != sig:
+            items = []
+            for e in live.values():
+                if len(e[4]) == 1:
+                    items.append((e[4][0].detach(), e[3], 0, 0))
+                else:
+                    items += [(p.detach(), e[3], 32, i) for i, p in enumerate(e[4])]
+            self._wplan = (sig, ops.CastPlan(items))
+        self._wplan[1].run()
+        for k, e in live.items():
+            self._wcache[k] = (e[0], tuple(p._version for p in e[4]), _GRAD_GEN[0], e[3], e[4])
 
     def invalidate_weight_cache(self):
         """Force a re-cast of every bf16 operand at the next forward. Needed only after an in-place weight update that

@@ -364,6 +364,39 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None):
     return out
 
 
+class CastPlan:
+    """A fixed list of (fp32 master -> bf16 operand) casts run as ONE launch (egom2p_cast_f32_to_bf16_multi): the per-step
+    refresh of the GEMM operands. items: (src (rows, cols) fp32 contiguous, dst bf16 2-D, group, slot)."""
+
+    def __init__(self, items):
+        import numpy as np
+        dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("rows", "<i8"), ("first_chunk", "<i8"), ("cols", "<i4"), ("dst_ld", "<i4"),
+                       ("group", "<i4"), ("slot", "<i4"), ("rows_per_chunk", "<i4"), ("pad", "<i4")])
+        assert dt.itemsize == 56
+        tab = np.zeros(len(items), dtype=dt)
+        chunk = 0
+        self.bytes = 0.0
+        self.ptrs = []
+        for i, (src, dst, group, slot) in enumerate(items):
+            _req(src, f32, "src"); _req(dst, bf16, "dst")
+            assert src.dim() == 2 and src.is_contiguous() and dst.dim() == 2 and dst.stride(1) == 1
+            rows, cols = src.shape
+            need_rows = rows if group == 0 else (rows + group - 1) // group * 2 * group
+            assert dst.shape[0] >= need_rows and dst.shape[1] >= cols, "cast plan: destination too small"
+            rpc = max(1, 8192 // cols)
+            tab[i] = (src.data_ptr(), dst.data_ptr(), rows, chunk, cols, dst.stride(0), group, slot, rpc, 0)
+            chunk += (rows + rpc - 1) // rpc
+            self.bytes += rows * cols * 6.0
+            self.ptrs.append((src.data_ptr(), dst.data_ptr()))
+        self.n_items, self.n_chunks = len(items), chunk
+        self.table = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).to(items[0][0].device)
+
+    def run(self):
+        lib = _lib.load()
+        with _timed("cast", self.bytes, "byte"):
+            _lib.check(lib.egom2p_cast_f32_to_bf16_multi(_p(self.table), self.n_items, self.n_chunks, _s()), "cast_f32_to_bf16_multi")
+
+
 def add_f32(a, b, want_f32=True, want_bf16=False):
     lib = _lib.load()
     out = torch.empty_like(a) if want_f32 else None

@@ -165,6 +165,20 @@ int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, con
 int egom2p_swiglu_fwd(const uint16_t* ab, int64_t rows, int32_t hidden, uint16_t* g, void* stream);
 int egom2p_swiglu_bwd(const uint16_t* ab, const uint16_t* dg, int64_t rows, int32_t hidden, uint16_t* dab, void* stream);
 int egom2p_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
+/* One launch for a list of casts: the per-step refresh of the bf16 GEMM operands from the fp32 master weights
+ * (the reference gets this from torch.autocast's weight cache, run_training_egom2p.py:716). Item i casts a contiguous
+ * (rows, cols) fp32 matrix into a bf16 matrix of row pitch dst_ld; group > 0 writes row r to row
+ * (r / group) * 2 * group + slot * group + r % group (the interleaved fc1 | fc3 operand of egom2p_gemm_swiglu_fwd).
+ * first_chunk = running sum of ceil(rows / rows_per_chunk) over the items before i; n_chunks = the total. The array
+ * lives in device memory. */
+typedef struct {
+  const float* src;
+  uint16_t* dst;
+  int64_t rows;
+  int64_t first_chunk;
+  int32_t cols, dst_ld, group, slot, rows_per_chunk, pad_;
+} egom2p_cast_item;
+int egom2p_cast_f32_to_bf16_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, void* stream);
 /* out = a + b (fp32), optional bf16 copy. */
 int egom2p_add_f32(const float* a, const float* b, int64_t n, float* out, uint16_t* out_bf16, void* stream);
 /* Fused AdamW over one flat fp32 tensor (torch.optim.AdamW semantics; egom2p/utils/optim_factory.py:206-226),

@@ -77,8 +77,13 @@ def test_loss_trajectory_follows_oracle():
         random.seed(0)
         model(mdc, 64, 48, loss_type="mod")
     blk = model.encoder[0]
-    wq = model._wcache[("e", 0, "qkv")][1]
+    wq = model._wcache[("e", 0, "qkv")][3]
     assert torch.equal(wq, blk.attn.qkv.weight.detach().to(torch.bfloat16))
-    w2 = model._wcache[("e", 0, "w2")][1]
+    w2 = model._wcache[("e", 0, "w2")][3]
     F = blk.mlp.fc2.weight.shape[1]
     assert torch.equal(w2[:, :F], blk.mlp.fc2.weight.detach().to(torch.bfloat16))
+    w13 = model._wcache[("e", 0, "w13")][3]
+    v = w13.view(-1, 2, 32, w13.shape[1])
+    Fh = blk.mlp.fc1.weight.shape[0]
+    assert torch.equal(v[:, 0].reshape(-1, w13.shape[1])[:Fh], blk.mlp.fc1.weight.detach().to(torch.bfloat16))
+    assert torch.equal(v[:, 1].reshape(-1, w13.shape[1])[:Fh], blk.mlp.fc3.weight.detach().to(torch.bfloat16))
