@@ -347,8 +347,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all nn.Linear fwd/dgrad/wgrad)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the qkv projection
-                         # launch at b = 16 (M = 32768, N = 2304, K = 768; algorithmic bytes 204.8 MB): profiles/r01b_ncu_summary.md
-                         "traffic": 148.6e6, "traffic_unit": "bytes per launch (M=32768 N=2304 K=768 projection, b=16)",
+                         # launch of this workload (b = 32: M = 65536, N = 2304, K = 768; algorithmic bytes 406 MB): profiles/r01e_gemm_ncu.md
+                         "traffic": 354.5e6, "traffic_unit": "bytes per launch (M=65536 N=2304 K=768 projection, b=32)",
                          "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                          "share_of_kernel_time": g["ms"] / max(total_kernel_ms, 1e-9),
                          "families": {k: {"ms": round(d["ms"], 3), "launches": d["launches"],

@@ -18,9 +18,14 @@ for r in rd:
 # the LAST step = everything after the previous step's optimizer launches (the first step of a process also holds one-off
 # launches -- optimizer-state zero fills, initial weight casts -- so cutting the list into equal parts would mis-attribute them)
 opt = [i for i, (n, _) in enumerate(rows) if "FusedOptimizer" in n or "adamw" in n.lower()]
-ends = [i for i in opt if i + 1 < len(rows) and i + 1 not in set(opt)]
-if ends:
-    last = rows[ends[-1] + 1:]
+runs = []   # contiguous groups of optimizer launches = one optimizer step each
+for i in opt:
+    if runs and i - runs[-1][1] <= 2:
+        runs[-1][1] = i
+    else:
+        runs.append([i, i])
+if len(runs) >= 2:
+    last = rows[runs[-2][1] + 1: runs[-1][1] + 1]
 else:
     per = len(rows) // nsteps
     last = rows[-per:]
