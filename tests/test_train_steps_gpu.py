@@ -87,3 +87,49 @@ def test_loss_trajectory_follows_oracle():
     Fh = blk.mlp.fc1.weight.shape[0]
     assert torch.equal(v[:, 0].reshape(-1, w13.shape[1])[:Fh], blk.mlp.fc1.weight.detach().to(torch.bfloat16))
     assert torch.equal(v[:, 1].reshape(-1, w13.shape[1])[:Fh], blk.mlp.fc3.weight.detach().to(torch.bfloat16))
+
+
+def test_loop_body_under_autocast_and_scaler():
+    """The reference calls the model under torch.cuda.amp.autocast(bfloat16) and steps through its GradScaler wrapper with
+    the scaler disabled for bf16 (run_training_egom2p.py:518,725-746; native_scaler.py:27-47). The module computes with its
+    own kernels, so that context must change nothing: same losses as the plain loop (fp32 atomics in dQ / embedding
+    gradients make later steps differ in the last bits only)."""
+    cfg = synth.make_cfg(192, 3, 2, 2, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"], video_vocab=512, video_thw=(5, 4, 4))
+    md = synth.make_batch(cfg, B=4, seed=12,
+                          n_in={"tok_cam": [5, 0, 30, 2], "tok_depth": [30, 10, 0, 1], "tok_gaze": [4, 0, 30, 0], "tok_rgb": [25, 40, 4, 0]},
+                          n_tgt={"tok_cam": [10, 30, 0, 1], "tok_depth": [20, 0, 40, 0], "tok_gaze": [3, 0, 0, 0], "tok_rgb": [15, 18, 70, 0]})
+    sd = synth.make_state_dict(cfg, 6)
+    mdc = to_cuda(md)
+
+    def loop(amp):
+        model = build_model(cfg).cuda()
+        model.load_state_dict(sd, strict=True)
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=LR, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+        scaler = torch.amp.GradScaler("cuda", enabled=False)
+        out = []
+        for s in range(3):
+            random.seed(200 + s)
+            if amp:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss, mod_loss = model({m: dict(d) for m, d in mdc.items()}, 64, 48, loss_type="mod")
+                assert loss.dtype == torch.float32 and all(v.dtype == torch.float32 for v in mod_loss.values())
+                scaler.scale(loss).backward()
+                scaler.unscale_(opt)
+                torch.nn.utils.clip_grad_norm_(params, 1.0)
+                scaler.step(opt)
+                scaler.update()
+            else:
+                loss, _ = model({m: dict(d) for m, d in mdc.items()}, 64, 48, loss_type="mod")
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(params, 1.0)
+                opt.step()
+            opt.zero_grad(set_to_none=True)
+            out.append(loss.item())
+        return out
+
+    plain, amp = loop(False), loop(True)
+    assert plain[0] == amp[0], (plain, amp)
+    for a, b in zip(plain, amp):
+        assert abs(a - b) <= 2e-4 * abs(a), (plain, amp)
+    assert plain[-1] < 0.95 * plain[0]
