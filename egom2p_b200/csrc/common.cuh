@@ -124,6 +124,29 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
+// ---- cluster launch control: a running cluster cancels a cluster of the same grid that has not started yet and takes over
+// its work item. The 16-byte response lands in the same shared-memory offset of every CTA of the cluster and completes 16
+// transaction bytes on each CTA's mbarrier at the same offset (semantics pinned by tools/micro/test_clc.cu). A failed
+// request (nothing left to cancel) must be the last one issued.
+__device__ __forceinline__ void clc_try_cancel_multicast(void* resp16, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(smem_u32(resp16)), "r"(smem_u32(bar)) : "memory");
+}
+// Decodes a response: true + blockIdx.x of the cancelled cluster's first CTA, or false when nothing was left to cancel.
+__device__ __forceinline__ bool clc_decode(const void* resp16, int& first_ctaid_x) {
+  uint32_t valid, x;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}\n"
+      : "=r"(x), "=r"(valid) : "r"(smem_u32(resp16)) : "memory");
+  first_ctaid_x = (int)x;
+  return valid != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

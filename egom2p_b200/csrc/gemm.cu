@@ -57,7 +57,8 @@ struct GemmSmem {
   static constexpr int kStages = BN == 256 ? 6 : 8;
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // one 32-row x 128-byte swizzled box per epilogue warp (a second
                                                           // box costs a pipeline stage: measured 9 % slower, tools/bench_gemm_cold.py)
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSched = 4;                         // cluster-launch-control response ring (work items in flight)
+  static constexpr int kBarBytes = kSched * 16 + (2 * kStages + 4 + 2 * kSched) * 8 + 16;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // + alignment slack
 };
 
@@ -83,11 +84,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::kABytes;
   uint8_t* staging = smem + kStages * S::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
+  constexpr int kSched = S::kSched;
+  uint4* clc_resp = reinterpret_cast<uint4*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(clc_resp + kSched);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* clc_full = tempty_bar + 2;     // response of the next work item landed (in every CTA of the pair)
+  uint64_t* clc_empty = clc_full + kSched; // leader's: every reader of both CTAs is done with the slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(clc_empty + kSched);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
@@ -97,11 +102,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // Pair mode: the two CTAs of a pair walk the same work items; rank r owns M tile 2 * pair + r (its 128 rows of A and of
   // the accumulator) and stages the rows [n0 + r * BN/2, +BN/2) of B. A pair past the last M tile still takes part in the
   // loads; its TMA reads are zero-filled and its stores are clipped.
+  // Work distribution: the grid holds one pair per work item; a pair starts on its own item and then keeps taking over the
+  // items of pairs that have not been launched yet (cluster launch control), so the kernel is persistent -- accumulators
+  // double-buffered across items -- without a static item -> SM assignment. With a static assignment one SM held by another
+  // resident kernel (NCCL's all-reduce under DDP) makes the displaced pair run its whole share after everybody else:
+  // 1.6x on the qkv projection (tools/bench_gemm_corun.py).
   constexpr int cl = 2;
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
-  const int worker = blockIdx.x / cl, n_workers = gridDim.x / cl;
-  const int total_items = ((m_tiles + cl - 1) / cl) * n_tiles * splits;
+  // One request per processed item, issued by the leader's producer warp when it starts the item; every role of both CTAs
+  // reads the response after its own work on the item. Returns false when nothing was left to take over.
+  auto next_item = [&](int it, int& item, bool is_scheduler) -> bool {
+    const int slot = it % kSched;
+    mbar_wait(&clc_full[slot], (it / kSched) & 1);
+    int x;
+    const bool valid = clc_decode(&clc_resp[slot], x);
+    fence_async_smem();   // the generic-proxy read is ordered before the async-proxy write of the slot's next response
+    __syncwarp();
+    if (lane == 0 && !is_scheduler) {
+      if (leader) mbar_arrive(&clc_empty[slot]);
+      else mbar_arrive_cluster(cluster_map(&clc_empty[slot], 0));
+    }
+    item = x / cl;
+    return valid;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -113,6 +137,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], cl * kEpiWarps);  // pair: the epilogue warps of both CTAs release the leader's barrier
+    }
+    for (int i = 0; i < kSched; ++i) {
+      mbar_init(&clc_full[i], 1);
+      mbar_init(&clc_empty[i], cl * kEpiWarps + 2);  // + the leader's MMA warp + the peer's producer warp
     }
     fence_mbar_init();
   }
@@ -130,7 +158,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // The whole warp walks the loop (addresses / coordinates stay in uniform registers); one elected lane issues.
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = worker; item < total_items; item += n_workers) {
+    int item = blockIdx.x / cl;
+    for (int it = 0;; ++it) {
+      if (leader) {  // ask for the item after this one now: the answer is there long before this item's k loop ends
+        const int slot = it % kSched;
+        if (elect_one()) {
+          mbar_wait(&clc_empty[slot], ((it / kSched) & 1) ^ 1);
+          mbar_expect_tx(&clc_full[slot], 16);
+          mbar_expect_tx_cluster(cluster_map(&clc_full[slot], 1), 16);
+          clc_try_cancel_multicast(&clc_resp[slot], &clc_full[slot]);
+        }
+        __syncwarp();
+      }
       const int tile = item / splits, split = item - tile * splits;
       const int m0 = ((tile / n_tiles) * cl + (int)crank) * BM, n0 = (tile % n_tiles) * BN;
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
@@ -159,6 +198,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (!next_item(it, item, leader)) break;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -168,8 +208,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr uint64_t kStepA = A_MN ? (2048 >> 4) : (32 >> 4), kStepB = B_MN ? (2048 >> 4) : (32 >> 4);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int item = worker; item < total_items && leader; item += n_workers, ++it) {  // pair: only the leader CTA issues
+    int item = blockIdx.x / cl;
+    for (int it = 0; leader; ++it) {  // pair: only the leader CTA issues
       const int split = item % splits;
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       const int acc = it & 1;
@@ -194,6 +234,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (!next_item(it, item, false)) break;
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -201,8 +242,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 2) >> 2;    // which half of the tile's columns
     uint8_t* box = staging + (warp - 2) * 4096;
     constexpr int kHalfCols = BN / 2;
-    int it = 0;
-    for (int item = worker; item < total_items; item += n_workers, ++it) {
+    int item = blockIdx.x / cl;
+    for (int it = 0;; ++it) {
       const int tile = item / splits;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -486,6 +527,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (leader) mbar_arrive(&tempty_bar[acc]);
         else mbar_arrive_cluster(cluster_map(&tempty_bar[acc], 0));
       }
+      if (!next_item(it, item, false)) break;
     }
     tma_store_wait_all();  // global writes complete before the CTA exits
   }
@@ -577,12 +619,7 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = S::kTotal; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
-  static int max_clusters = 0;
-  if (!max_clusters) {
-    cfg.gridDim = dim3(2 * (sms / 2));
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) max_clusters = sms / 2 - 2;
-  }
-  cfg.gridDim = dim3(2 * (pair_items < max_clusters ? pair_items : max_clusters));
+  cfg.gridDim = dim3(2 * pair_items);   // one pair per work item; the pairs that get to run cancel and absorb the rest
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmCb, tmCf, p);
   if (e != cudaSuccess) { set_error("gemm: cluster launch: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
   return check_launch("gemm_bf16");
