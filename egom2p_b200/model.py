@@ -111,7 +111,8 @@ class DecoderBlock(nn.Module):
 # =============================================================================================== kernels glue
 class _Geom:
     """Shapes + key-range tables of one forward (device tensors, no host syncs)."""
-    __slots__ = ("B", "N", "M", "H", "D", "enc_lo", "enc_hi", "dec_lo", "dec_hi", "x_lo", "x_hi", "eps", "m_enc", "m_dec", "m_x")
+    __slots__ = ("B", "N", "M", "H", "D", "enc_lo", "enc_hi", "dec_lo", "dec_hi", "x_lo", "x_hi", "eps", "m_enc", "m_dec", "m_x",
+                 "ctx_users", "dctx_acc")
 
     def build_meta(self, dev, encoder: bool = True):
         """Range metadata per attention kind, once per forward (shared by all layers, heads, fwd and bwd)."""
@@ -139,6 +140,20 @@ def _split_w13_grad(dw13, F):
     return v[:, 0].reshape(Fp, D)[:F], v[:, 1].reshape(Fp, D)[:F]
 
 
+def _with_bf16(dx, dxb):
+    """Hands the bf16 copy of a residual-stream gradient (written by the LayerNorm backward that produced it, for 1/3 of the
+    traffic of a separate cast pass) to the next backward node: autograd passes the same tensor object on, attributes included."""
+    dx._egom2p_bf16 = dxb
+    return dx
+
+
+def _bf16_of(dx):
+    dxb = getattr(dx, "_egom2p_bf16", None)
+    if dxb is not None and dxb.shape == dx.shape and dxb.device == dx.device and dxb.dtype == bf16:
+        return dxb
+    return ops.cast_bf16(dx)
+
+
 def _mlp_fwd(x1, n2w, w13, w2, eps):
     h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, eps)
     ab, g = ops.gemm_swiglu_fwd(h2, w13)   # fc1|fc3 GEMM with the SwiGLU gate in its epilogue
@@ -149,7 +164,7 @@ def _mlp_fwd(x1, n2w, w13, w2, eps):
 def _mlp_bwd(dx2, x1, n2w, w13, w2, saved):
     """Returns dx1 (incl. the residual path), its bf16 copy, dn2w, dw13, dw2."""
     mean2, rstd2, h2, ab, g = saved
-    dx2b = ops.cast_bf16(dx2)
+    dx2b = _bf16_of(dx2)
     dw2 = ops.linear_wgrad(dx2b, g)
     dab = ops.gemm_swiglu_bwd(dx2b, w2, ab)   # fc2 dgrad with the SwiGLU derivative in its epilogue
     dw13 = ops.linear_wgrad(dab, h2)
@@ -179,8 +194,8 @@ def _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, saved, B, L, H, meta):
     dwqkv = ops.linear_wgrad(dqkv, h1)
     dh1 = ops.linear_dgrad(dqkv, wqkv)
     dn1w = _zeros(n1w.numel(), x.device)
-    dx, _ = ops.layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx_in=dx1, d_weight=dn1w)
-    return dx, dn1w, dwqkv, dwproj
+    dx, dxb = ops.layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx_in=dx1, d_weight=dn1w, want_bf16=True)
+    return _with_bf16(dx, dxb), dn1w, dwqkv, dwproj
 
 
 class _EncoderBlockFn(torch.autograd.Function):
@@ -227,6 +242,8 @@ class _DecoderBlockFn(torch.autograd.Function):
         y2 = ops.linear_fwd(o2, wxproj, addend=y1, out_dtype=f32)
         y3, sm = _mlp_fwd(y2, n2w, w13, w2, g.eps)
         ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
+        ctx.ctx_key = context.data_ptr()
+        g.ctx_users += 1
         ctx.save_for_backward(y, context, n1w, qnw, cnw, n2w, y1, y2, meanq, rstdq, hq, q, meanc, rstdc, hc, kv, o2, lse2,
                               *sa, *sm)
         return y3
@@ -254,7 +271,22 @@ class _DecoderBlockFn(torch.autograd.Function):
         dhc = ops.linear_dgrad(dkv, wkv)
         dqnw, dcnw = _zeros(D, dev), _zeros(D, dev)
         dy1, dy1b = ops.layernorm_bwd(dhq, y1, qnw, meanq, rstdq, dx_in=dy2, d_weight=dqnw, want_bf16=True)
-        dctx, _ = ops.layernorm_bwd(dhc, context, cnw, meanc, rstdc, d_weight=dcnw)
+        # All decoder blocks read the same `context`: instead of letting autograd add twelve (B*N, D) fp32 gradients pairwise,
+        # each block's context_norm backward adds the running sum in its own pass (dx_in) and only the block that runs last
+        # returns it. Falls back to one gradient per block whenever the bookkeeping does not match a plain single backward.
+        acc = g.dctx_acc
+        chained = g.ctx_users > 0 and (acc is None or (acc[0] == ctx.ctx_key and acc[1].shape == context.shape))
+        last = chained and g.ctx_users == 1
+        dctx, dctxb = ops.layernorm_bwd(dhc, context, cnw, meanc, rstdc, dx_in=acc[1] if (chained and acc is not None) else None,
+                                        d_weight=dcnw, want_bf16=last)
+        if chained:
+            g.ctx_users -= 1
+            if last:
+                g.dctx_acc = None
+                dctx = _with_bf16(dctx, dctxb)
+            else:
+                g.dctx_acc = (ctx.ctx_key, dctx)
+                dctx = None
         dy, dn1w, dwqkv, dwsproj = _self_attn_bwd(dy1, dy1b, y, n1w, wqkv, wsproj, sa, g.B, g.M, g.H, g.m_dec)
         F = ctx.F
         d1, d3 = _split_w13_grad(dw13, F)
@@ -277,13 +309,13 @@ class _ContextFn(torch.autograd.Function):
         _GRAD_GEN[0] += 1
         x, norm_w, mean, rstd, h = ctx.saved_tensors
         dctx = dctx.contiguous()
-        dcb = ops.cast_bf16(dctx)
+        dcb = _bf16_of(dctx)
         dw = ops.linear_wgrad(dcb, h)
         db = ops.colsum(dctx, _zeros(dctx.shape[1], dctx.device))
         dh = ops.linear_dgrad(dcb, ctx.wb)
         dnw = _zeros(norm_w.numel(), x.device)
-        dx, _ = ops.layernorm_bwd(dh, x, norm_w, mean, rstd, d_weight=dnw)
-        return dx, dctx, dnw, dw, db, None, None
+        dx, dxb = ops.layernorm_bwd(dh, x, norm_w, mean, rstd, d_weight=dnw, want_bf16=True)
+        return _with_bf16(dx, dxb), dctx, dnw, dw, db, None, None
 
 
 class _EmbedFn(torch.autograd.Function):
@@ -380,8 +412,8 @@ class _HeadLossFn(torch.autograd.Function):
             ops.scatter_rows_f32(dym, idx, dyn)
             dws.append(dw)
         dnw = _zeros(D, dev)
-        dy, _ = ops.layernorm_bwd(dyn, y, norm_w, mean, rstd, d_weight=dnw)
-        return (dy, dnw, None, None, None, None, *dws)
+        dy, dyb = ops.layernorm_bwd(dyn, y, norm_w, mean, rstd, d_weight=dnw, want_bf16=True)
+        return (_with_bf16(dy, dyb), dnw, None, None, None, None, *dws)
 
 
 # =============================================================================================== the module
@@ -653,6 +685,7 @@ class EgoM2P(nn.Module):
         g.B, g.N, g.M, g.H, g.D, g.eps = B, N, M, self.num_heads, self.dim, self.eps
         g.enc_lo = g.enc_hi = g.dec_lo = g.dec_hi = g.x_lo = g.x_hi = None
         g.m_enc = g.m_dec = g.m_x = None
+        g.ctx_users, g.dctx_acc = 0, None   # decoder blocks of this forward that read `context` / their running gradient
         return g
 
     # ------------------------------------------------------------------ the training step (reference :683-734)
