@@ -114,7 +114,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = s_free + 1;   // [2]
   uint64_t* pv_done = p_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-  int* s_range = reinterpret_cast<int*>(tmem_slot + 1);  // [0] = lo, [1] = hi
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
@@ -122,42 +121,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int trow = quarter * 32 + lane;  // row inside the tile (== TMEM lane)
   const int row = q0 + trow;
 
-  if (threadIdx.x == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < kFwdStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
     mbar_init(s_free, kAttnComputeWarps);
     for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], kAttnComputeWarps); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
-    s_range[0] = INT_MAX;
-    s_range[1] = INT_MIN;
+    // the Q tile does not depend on the key range: its load overlaps the range metadata reads and the TMEM allocation
+    mbar_expect_tx(q_full, kT * 128);
+    tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
   }
   if (warp == kMmaWarp) tmem_alloc<128>(tmem_slot);
-  __syncthreads();
-
   int lo = INT_MAX, hi = INT_MIN;
   float rscale = 0.f;
-  if (warp < kAttnComputeWarps && row < p.Mq) {
+  if (warp < kAttnComputeWarps && row < p.Mq) {   // the row's range: in flight while the barriers / TMEM are set up
     lo = p.meta.row_lo[(int64_t)b * p.S + row];
     hi = p.meta.row_hi[(int64_t)b * p.S + row];
     rscale = p.meta.row_scale[(int64_t)b * p.S + row];
-    if (half == 0 && hi > lo) { atomicMin(&s_range[0], lo); atomicMax(&s_range[1], hi); }
   }
+  // key range of the whole tile = union of its two 64-row blocks (precomputed by attn_blocks_kernel over the same rows)
+  const int64_t bo = (int64_t)b * (p.S / 64) + 2 * blockIdx.x;
+  const int lo_cta = min(p.meta.blk_lo[bo], p.meta.blk_lo[bo + 1]), hi_cta = max(p.meta.blk_hi[bo], p.meta.blk_hi[bo + 1]);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int lo_cta = s_range[0], hi_cta = s_range[1];
   const int nblk = hi_cta > lo_cta ? (hi_cta - lo_cta + kBlk - 1) / kBlk : 0;
 
   if (warp == kTmaWarp) {
     // warp-uniform control flow (operands stay in uniform registers); one elected lane issues the copies
+    if (nblk == 0) mbar_wait(q_full, 0);   // nobody else consumes the early Q load: it must land before the CTA exits
     if (nblk > 0) {
-      if (elect_one()) {
-        mbar_expect_tx(q_full, kT * 128);
-        tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
-      }
-      __syncwarp();
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kFwdStages;
         mbar_wait(&kv_empty[st], ((j / kFwdStages) & 1) ^ 1);

@@ -120,7 +120,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
   const int nqb = p.S / kT;
-  if (threadIdx.x == 0) {
+  if (warp == kBwdTmaWarp && lane == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < kBwdStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(s_full, 1);   mbar_init(s_free, kBwdMathWarps);
@@ -130,6 +130,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(dq_full, 1);  mbar_init(dq_free, 4);
     mbar_init(dkv_full, 1);
     fence_mbar_init();
+    // the K / V tile does not depend on the query-block list: its load overlaps the list build and the TMEM allocation
+    mbar_expect_tx(kv_full, 2 * BwdSmem::kTile);
+    tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
+    tma_load_2d(sV, &tmV, kv_full, h * kD, b * p.Nk + kv0);
   }
   if (warp == 0) {  // 128-query blocks whose key ranges intersect this key tile (ballot-compacted, ascending)
     int n = 0;
@@ -162,13 +166,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp >= kBwdTmaWarp) {
     if (warp == kBwdTmaWarp) {
       // ------------------------------------------------------------------------------------------ TMA producer
+      if (n == 0) mbar_wait(kv_full, 0);   // nobody else consumes the early K / V load: it must land before the CTA exits
       if (n > 0) {
-        if (elect_one()) {
-          mbar_expect_tx(kv_full, 2 * BwdSmem::kTile);
-          tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
-          tma_load_2d(sV, &tmV, kv_full, h * kD, b * p.Nk + kv0);
-        }
-        __syncwarp();
         for (int idx = 0; idx < n; ++idx) {
           const int st = idx % kBwdStages;
           const int r0 = (int)(s_list[idx] & 0x3fff) * kT;
