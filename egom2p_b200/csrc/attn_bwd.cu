@@ -135,6 +135,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
     tma_load_2d(sV, &tmV, kv_full, h * kD, b * p.Nk + kv0);
   }
+  // One query block's loads (Q, dO and the five per-row metadata vectors) into ring stage st.
+  auto issue_q_block = [&](int qblk, int st) {
+    const int r0 = qblk * kT;
+    uint8_t* meta = sMeta + st * kBwdMetaBytes;
+    const int64_t hoff = ((int64_t)b * p.H + h) * p.S + r0, roff = (int64_t)b * p.S + r0;
+    mbar_expect_tx(&q_full[st], 2 * BwdSmem::kTile + kBwdMetaBytes);
+    tma_load_2d(sQ + st * BwdSmem::kTile, &tmQ, &q_full[st], h * kD, b * p.Mq + r0);
+    tma_load_2d(sDO + st * BwdSmem::kTile, &tmDO, &q_full[st], h * kD, b * p.Mq + r0);
+    bulk_load(meta + 0 * 512, p.lse2 + hoff, 512, &q_full[st]);
+    bulk_load(meta + 1 * 512, p.ndelta + hoff, 512, &q_full[st]);
+    bulk_load(meta + 2 * 512, p.meta.row_lo + roff, 512, &q_full[st]);
+    bulk_load(meta + 3 * 512, p.meta.row_hi + roff, 512, &q_full[st]);
+    bulk_load(meta + 4 * 512, p.meta.row_scale + roff, 512, &q_full[st]);
+  };
+  if (warp == kBwdTmaWarp) {
+    // The first query block of the list, found by this warp on its own (same test as the list build below), so that its
+    // loads are in flight before the set-up barrier instead of one round trip after it.
+    int first = -1;
+    for (int i0 = 0; i0 < nqb && first < 0; i0 += 32) {
+      const int i = i0 + lane;
+      bool take = false;
+      if (i < nqb) {
+        const int64_t o = ((int64_t)b * nqb + i) * 2;
+        const int lo = min(p.meta.blk_lo[o], p.meta.blk_lo[o + 1]), hi = max(p.meta.blk_hi[o], p.meta.blk_hi[o + 1]);
+        take = hi > kv0 && lo < kv0 + kT;
+      }
+      const unsigned msk = __ballot_sync(0xffffffffu, take);
+      if (msk) first = i0 + __ffs(msk) - 1;
+    }
+    __syncwarp();   // lane 0's barrier initialisation above is ordered before its own issue below
+    if (first >= 0 && lane == 0) issue_q_block(first, 0);
+  }
   if (warp == 0) {  // 128-query blocks whose key ranges intersect this key tile (ballot-compacted, ascending)
     int n = 0;
     for (int i0 = 0; i0 < nqb; i0 += 32) {
@@ -168,22 +200,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ------------------------------------------------------------------------------------------ TMA producer
       if (n == 0) mbar_wait(kv_full, 0);   // nobody else consumes the early K / V load: it must land before the CTA exits
       if (n > 0) {
-        for (int idx = 0; idx < n; ++idx) {
+        for (int idx = 1; idx < n; ++idx) {   // block 0 was issued before the set-up barrier
           const int st = idx % kBwdStages;
-          const int r0 = (int)(s_list[idx] & 0x3fff) * kT;
           mbar_wait(&q_empty[st], ((idx / kBwdStages) & 1) ^ 1);
-          uint8_t* meta = sMeta + st * kBwdMetaBytes;
-          const int64_t hoff = ((int64_t)b * p.H + h) * p.S + r0, roff = (int64_t)b * p.S + r0;
-          if (elect_one()) {
-            mbar_expect_tx(&q_full[st], 2 * BwdSmem::kTile + kBwdMetaBytes);
-            tma_load_2d(sQ + st * BwdSmem::kTile, &tmQ, &q_full[st], h * kD, b * p.Mq + r0);
-            tma_load_2d(sDO + st * BwdSmem::kTile, &tmDO, &q_full[st], h * kD, b * p.Mq + r0);
-            bulk_load(meta + 0 * 512, p.lse2 + hoff, 512, &q_full[st]);
-            bulk_load(meta + 1 * 512, p.ndelta + hoff, 512, &q_full[st]);
-            bulk_load(meta + 2 * 512, p.meta.row_lo + roff, 512, &q_full[st]);
-            bulk_load(meta + 3 * 512, p.meta.row_hi + roff, 512, &q_full[st]);
-            bulk_load(meta + 4 * 512, p.meta.row_scale + roff, 512, &q_full[st]);
-          }
+          if (elect_one()) issue_q_block((int)(s_list[idx] & 0x3fff), st);
           __syncwarp();
         }
       }
