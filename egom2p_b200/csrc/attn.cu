@@ -143,17 +143,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // key range of the whole tile = union of its two 64-row blocks (precomputed by attn_blocks_kernel over the same rows)
   const int64_t bo = (int64_t)b * (p.S / 64) + 2 * blockIdx.x;
   const int lo_cta = min(p.meta.blk_lo[bo], p.meta.blk_lo[bo + 1]), hi_cta = max(p.meta.blk_hi[bo], p.meta.blk_hi[bo + 1]);
+  const int nblk = hi_cta > lo_cta ? (hi_cta - lo_cta + kBlk - 1) / kBlk : 0;
+  if (warp == kTmaWarp && lane == 0 && nblk > 0) {   // first K / V block: in flight before the set-up barrier as well
+    mbar_expect_tx(&kv_full[0], 2 * kBlk * 128);
+    tma_load_2d(sK, &tmK, &kv_full[0], h * kD, b * p.Nk + lo_cta);
+    tma_load_2d(sV, &tmV, &kv_full[0], h * kD, b * p.Nk + lo_cta);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int nblk = hi_cta > lo_cta ? (hi_cta - lo_cta + kBlk - 1) / kBlk : 0;
 
   if (warp == kTmaWarp) {
     // warp-uniform control flow (operands stay in uniform registers); one elected lane issues the copies
     if (nblk == 0) mbar_wait(q_full, 0);   // nobody else consumes the early Q load: it must land before the CTA exits
     if (nblk > 0) {
-      for (int j = 0; j < nblk; ++j) {
+      for (int j = 1; j < nblk; ++j) {
         const int st = j % kFwdStages;
         mbar_wait(&kv_empty[st], ((j / kFwdStages) & 1) ^ 1);
         const int krow = b * p.Nk + lo_cta + j * kBlk;
