@@ -36,15 +36,17 @@ N_ENC = N_DEC = 2048
 SPLIT = {"tok_rgb": 1009, "tok_depth": 1009, "tok_cam": 15, "tok_gaze": 15}
 # algorithmic (mask-aware) FLOPs of one sample-step in the dense regime, SURVEY.md section 8(d): 3 x 1396.9 GFLOP
 FLOP_PER_SAMPLE_STEP = 4190.6e9
+# tokens per sample and vocabulary of each modality (egom2p/data/modality_info.py: tok_rgb / tok_depth = Cosmos DV4x8x8
+# 5 x 32 x 32 tokens of a 64k codebook, tok_cam / tok_gaze = 30 tokens of a 256 codebook)
+SHAPES = {"tok_cam": (30, 256), "tok_depth": (5120, 64000), "tok_gaze": (30, 256), "tok_rgb": (5120, 64000)}
 
 
 def make_batch(b: int, seed: int, pin: bool):
     """Synthetic mod_dict in the reference layout (egom2p/data/masking.py:236-266), CPU tensors."""
-    from egom2p_b200.modality_info import MODALITY_INFO as MI
     rng = np.random.default_rng(seed)
     md = {}
-    for m in sorted(MI):
-        L, V = MI[m]["max_tokens"], MI[m]["vocab_size"]
+    for m in sorted(SHAPES):
+        L, V = SHAPES[m]
         n = SPLIT[m]
         ids = rng.integers(0, V, size=(b, L), dtype=np.int64)
         imask = np.ones((b, L), dtype=bool)
@@ -71,14 +73,13 @@ def load_ref_masks():
 
 
 def make_batch_ref_masks(b: int, offset: int, seed: int, pin: bool, g=None):
-    from egom2p_b200.modality_info import MODALITY_INFO as MI
     g = load_ref_masks() if g is None else g
     rng = np.random.default_rng(seed)
     n = int(g["n"])
     sel = [(offset + i) % n for i in range(b)]
     md = {}
-    for m in sorted(MI):
-        L, V = MI[m]["max_tokens"], MI[m]["vocab_size"]
+    for m in sorted(SHAPES):
+        L, V = SHAPES[m]
         t = torch.from_numpy(rng.integers(0, V, size=(b, L), dtype=np.int64))
         if L == 5120:
             t = t.reshape(b, 5, 32, 32)
@@ -160,7 +161,50 @@ def build_model(device):
                            encoder_embeddings={k: MI[k]["encoder_embedding"]() for k in mods},
                            decoder_embeddings={k: MI[k]["decoder_embedding"]() for k in mods},
                            modality_info={k: MI[k] for k in mods}, num_register_tokens=0)
+    # random-init ego-b weights: the deterministic draw the full-size parity fixtures were generated with (the reference's
+    # init distributions, oracle/synth.make_state_dict seed 0), so the parity gate checks the very model that is timed
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gen_golden_egob as gg
+    import synth
+    model.load_state_dict(synth.make_state_dict(gg.egob_cfg(), gg.SD_SEED), strict=True)
     return model.to(device)
+
+
+def parity_gate(model, dev):
+    """The b = 1 full-size parity check of tests/test_egob_fullsize_gpu.py, run on the model that is about to be timed
+    ("parity gates run beside the timing"): loss / logits / gradient norms against the outputs of the
+    UNMODIFIED reference in fp32 (tests/golden/egob_dense.npz, made by oracle/gen_golden_egob.py). oracle/ is used here as
+    the checker only (deterministic weights + batch builders); nothing of it is timed."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gen_golden_egob as gg
+    g = np.load(os.path.join(ROOT, "tests", "golden", "egob_dense.npz"))
+    cfg = gg.egob_cfg()
+    md = {m: {k: v.to(dev) for k, v in d.items()} for m, d in gg.dense_batch(cfg).items()}
+    model.zero_grad(set_to_none=True)
+    random.seed(gg.SHUFFLE_SEED)
+    loss, mod_loss = model(md, N_ENC, N_DEC, loss_type="mod")
+    loss.backward()
+    ref = float(g["loss"])
+    norms = dict(zip(g["grad_names"], g["grad_norms"]))
+    gerr = max(abs(p.grad.double().norm().item() - norms[n]) / (norms[n] + 1e-12) for n, p in model.named_parameters())
+    model.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        random.seed(gg.SHUFFLE_SEED)
+        logits = model(md, N_ENC, N_DEC, return_logits=True)
+    cols = torch.from_numpy(g["cols"]).to(dev)
+    lerr = {}
+    for m in gg.MODS:
+        rows = torch.from_numpy(g[f"rows::{m}"].astype(np.int64)).to(dev)
+        lg = logits[m][0].index_select(0, rows).float()
+        got = lg if lg.shape[-1] <= 256 else lg.index_select(1, cols)
+        lerr[m] = float((got - torch.from_numpy(g[f"logits::{m}"]).to(dev)).abs().max())
+    del logits
+    out = {"case": "ego-b b=1 N=M=2048 dense split vs the unmodified reference in fp32 (tests/golden/egob_dense.npz)",
+           "loss": float(loss), "loss_reference": ref, "loss_rel_err": abs(float(loss) - ref) / abs(ref),
+           "logits_max_abs_err": lerr, "grad_norm_max_rel_err": gerr, "tolerances": {"loss_rel": 1e-3, "logits": 2e-2, "grad": 5e-2}}
+    out["pass"] = bool(out["loss_rel_err"] < 1e-3 and max(lerr.values()) < 2e-2 and gerr < 5e-2)
+    return out
 
 
 def peaks():
@@ -171,26 +215,42 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+_CPU_REF = {}
+
+
 def cpu_reference_step(b: int, threads: int):
-    """One fwd+bwd of the CPU fp32 restatement (oracle/) on ego-b, dense regime, batch b. Returns seconds."""
+    """One training step (fwd + bwd + clip_grad_norm_(1.0) + AdamW, the same body the GPU arm times) of the CPU fp32
+    restatement (oracle/) on ego-b, dense regime, batch b, on `threads` host threads. Returns (seconds, loss). Weights and
+    optimizer state persist across calls; building them is not timed."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import egom2p_oracle as orc
     import synth
     torch.set_num_threads(threads)
-    cfg = synth.make_cfg(768, 12, 12, 12, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"])
-    sd = synth.make_state_dict(cfg, 0)
-    leaf = {}
-    for k, v in sd.items():
-        if k.endswith("to_logits.weight") or (k.startswith("decoder_embeddings") and k.endswith("mod_emb")):
-            continue
-        leaf[k] = v.requires_grad_(v.is_floating_point() and not k.endswith("pos_emb") and not (k.endswith(".bias") and "proj_context" not in k))
-    for m in cfg["mods"]:
-        leaf[f"decoder_embeddings.{m}.to_logits.weight"] = leaf[f"decoder_embeddings.{m}.token_emb.weight"]
-        leaf[f"decoder_embeddings.{m}.mod_emb"] = leaf[f"encoder_embeddings.{m}.mod_emb"]
-    md = make_batch(b, 1234, pin=False)
+    if "leaf" not in _CPU_REF:
+        cfg = synth.make_cfg(768, 12, 12, 12, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"])
+        sd = synth.make_state_dict(cfg, 0)
+        leaf = {}
+        for k, v in sd.items():
+            if k.endswith("to_logits.weight") or (k.startswith("decoder_embeddings") and k.endswith("mod_emb")):
+                continue
+            leaf[k] = v.requires_grad_(v.is_floating_point() and not k.endswith("pos_emb") and not (k.endswith(".bias") and "proj_context" not in k))
+        train = {k: v for k, v in leaf.items() if v.requires_grad}
+        opt = torch.optim.AdamW([{"params": [v for k, v in train.items() if not ("norm" in k or k.endswith(".bias"))], "weight_decay": 0.05},
+                                 {"params": [v for k, v in train.items() if ("norm" in k or k.endswith(".bias"))], "weight_decay": 0.0}],
+                                lr=1e-4, betas=(0.9, 0.95), eps=1e-8)
+        for m in cfg["mods"]:
+            leaf[f"decoder_embeddings.{m}.to_logits.weight"] = leaf[f"decoder_embeddings.{m}.token_emb.weight"]
+            leaf[f"decoder_embeddings.{m}.mod_emb"] = leaf[f"encoder_embeddings.{m}.mod_emb"]
+        _CPU_REF.update(cfg=cfg, leaf=leaf, train=list(train.values()), opt=opt, n=0)
+    r = _CPU_REF
+    md = make_batch(b, 1234 + r["n"], pin=False)
+    r["n"] += 1
     t0 = time.perf_counter()
-    out = orc.forward(leaf, cfg, md, N_ENC, N_DEC)
+    out = orc.forward(r["leaf"], r["cfg"], md, N_ENC, N_DEC)
     out["loss"].backward()
+    torch.nn.utils.clip_grad_norm_(r["train"], 1.0)
+    r["opt"].step()
+    r["opt"].zero_grad(set_to_none=True)
     return time.perf_counter() - t0, float(out["loss"])
 
 
@@ -209,10 +269,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ego-b mod4 train nominal tokens/sec (whole job)", "value": val, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ego-b mod4 (396.2M) train step fwd+bwd, dense regime 2048 enc + 2048 dec tokens, CPU fp32",
+            "config": {"workload": "ego-b mod4 (396.2M) training step: fwd + bwd + clip_grad_norm(1.0) + AdamW, dense regime 2048 enc + 2048 dec "
+                                   "tokens/sample, CPU fp32 (oracle port of the reference), 1 sample per step",
                        "global_batch": 1},
             "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port",
-                             "sample": "1 sample (4096 nominal tokens) fwd+bwd per step, oracle/egom2p_oracle.py (CPU fp32 restatement of the reference)"},
+                             "sample": "1 sample (4096 nominal tokens) per step, fwd + bwd + clip + AdamW, oracle/egom2p_oracle.py (CPU fp32 restatement of the reference)"},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -227,6 +288,9 @@ def main():
     ap.add_argument("--regime", default="dense", choices=["dense", "reference-masks"],
                     help="dense: SURVEY 8(d) headline synthetic regime; reference-masks: ragged masks drawn by the reference's UnifiedMasking")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the b = 1 full-size parity gate against the reference's fp32 outputs")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip timing the unmodified reference (baseline/_ref, eager bf16 autocast) on this GPU (N = 1 only)")
     ap.add_argument("--cpu-steps", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -260,13 +324,15 @@ def main():
                             lr=1e-4, betas=(0.9, 0.95), eps=1e-8, fused=True)
     params = list(model.parameters())
 
+    # a fresh batch for every warm-up and timed step (seed = 1234 + rank * 1000 + step): nothing to memorise
+    nb = args.warmup + args.steps
     if args.regime == "dense":
-        host_batches = [make_batch(b, 1234 + rank * 1000 + s, pin=True) for s in range(2)]
+        host_batches = [make_batch(b, 1234 + rank * 1000 + s, pin=True) for s in range(nb)]
         flops_per_step = b * FLOP_PER_SAMPLE_STEP
     else:
         gm = load_ref_masks()
-        host_batches = [make_batch_ref_masks(b, (rank * 2 + s) * b, 1234 + rank * 1000 + s, pin=True, g=gm) for s in range(2)]
-        flops_per_step = float(np.mean([step_flops(hb) for hb in host_batches]))
+        host_batches = [make_batch_ref_masks(b, (rank * nb + s) * b, 1234 + rank * 1000 + s, pin=True, g=gm) for s in range(nb)]
+        flops_per_step = float(np.mean([step_flops(hb) for hb in host_batches[args.warmup:]]))
     dev_batches = [{m: {k: v.to(dev) for k, v in d.items()} for m, d in hb.items()} for hb in host_batches]
 
     def step(md):
@@ -295,20 +361,23 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- parity gate on the model about to be timed (b = 1, full size, against the unmodified reference's fp32 outputs)
+    parity = parity_gate(model, dev) if not args.no_parity else None
+
     # ---- warm-up, then device-resident timing
     for i in range(args.warmup):
-        step(dev_batches[i % 2])
+        step(dev_batches[i])
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = _lib.launch_count()
-    ms = timed(lambda i: step(dev_batches[i % 2]), args.steps)
+    ms = timed(lambda i: step(dev_batches[args.warmup + i]), args.steps)
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if sampler else None
 
     # ---- end-to-end through the public API: pinned host inputs copied every step, loss read back every step
     def e2e_step(i):
-        md = {m: {k: v.to(dev, non_blocking=True) for k, v in d.items()} for m, d in host_batches[i % 2].items()}
+        md = {m: {k: v.to(dev, non_blocking=True) for k, v in d.items()} for m, d in host_batches[args.warmup + i].items()}
         loss = step(md)
         return loss.item()
     e2e_step(0)
@@ -347,6 +416,7 @@ def main():
                        "mfu_vs_measured_sustained": tflops / tf_sus, "peaks_source": src, "loss": last_loss},
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": md_bytes(host_batches[0]), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
+            "parity": parity,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all nn.Linear fwd/dgrad/wgrad)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
@@ -365,7 +435,29 @@ def main():
             dts = [cpu_reference_step(1, cores)[0] for _ in range(args.cpu_steps)]
             dt = float(np.mean(dts))
             line["cpu_baseline"] = {"value": NOMINAL_TOKENS / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_steps} x (1 sample = 4096 nominal tokens, fwd+bwd, fp32) of the same dense workload via oracle/egom2p_oracle.py"}
+                                    "sample": f"{args.cpu_steps} x (1 sample = 4096 nominal tokens, fwd + bwd + clip + AdamW, fp32) of the same dense workload via oracle/egom2p_oracle.py"}
+        if world == 1 and not args.no_reference_gpu:
+            # the bar to beat: the unmodified reference on this same GPU (baseline/ref_gpu.py); our model is released first
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import ref_gpu
+            if ref_gpu.available():
+                del opt, params, net, model, dev_batches
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                res = []
+                for rb in (4, 8):
+                    try:
+                        res.append(ref_gpu.time_reference(rb, 20, 5, dev, make_batch))
+                    except torch.cuda.OutOfMemoryError:
+                        res.append({"batch_per_gpu": rb, "oom": True})
+                        torch.cuda.empty_cache()
+                line["reference_gpu"] = res
+                best = max((r["tokens_per_s"] for r in res if "tokens_per_s" in r), default=None)
+                if best:
+                    line["reference_gpu_speedup"] = value / best
+            else:
+                line["reference_gpu"] = {"unavailable": "baseline/_ref/egom2p missing (tools/install_reference.py)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

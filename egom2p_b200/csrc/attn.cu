@@ -368,12 +368,8 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
     tmK = tmQ;
     tmV = tmQ;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
-    if (e != cudaSuccess) { set_error("attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  if ((rc = ensure_dyn_smem(attn_fwd_kernel, FwdSmem::kTotal, attr_done, "attn_fwd"))) return rc;
   dim3 grid((Mq + kT - 1) / kT, H, B);
   attn_fwd_kernel<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   return check_launch("attn_fwd");

@@ -641,12 +641,8 @@ extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint1
   if (Nk > 0) {
     EGO_REQUIRE(K && V && dK && dV, "attn_bwd: K / V / dK / dV missing");
     EGO_REQUIRE(lddk % 8 == 0 && lddv % 8 == 0 && ((uintptr_t)dK & 15) == 0 && ((uintptr_t)dV & 15) == 0, "attn_bwd: dK/dV alignment");
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal);
-      if (e != cudaSuccess) { set_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
-      attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    if ((rc = ensure_dyn_smem(attn_bwd_kernel, BwdSmem::kTotal, attr_done, "attn_bwd"))) return rc;
     CUtensorMap tmQ, tmDO, tmK, tmV, tmDQ;
     if ((rc = make_tmap_bf16_2d(&tmQ, Q, (uint64_t)B * Mq, (uint64_t)H * kD, ldq, kT, kD))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmDO, dO, (uint64_t)B * Mq, (uint64_t)H * kD, ldo, kT, kD))) return rc;

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <cstdio>
 
 #include "../../include/egom2p_b200.h"
@@ -30,6 +31,37 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // Same for 2-byte (bf16) or 4-byte (fp32) elements; box_cols * elem_bytes must be 128.
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function attribute and the library may be entered
+// from several threads (autograd runs backward on its own thread): one atomic bit per device ordinal, set after the
+// attribute call succeeded; a racing second thread at worst repeats the (idempotent) call.
+template <typename Kern>
+static inline int ensure_dyn_smem(Kern kern, int bytes, std::atomic<uint64_t>& done, const char* what) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d B smem): %s", what, bytes, cudaGetErrorString(e));
+    return EGOM2P_ERR_CUDA;
+  }
+  done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+// SM count of the current device (cached per device ordinal).
+static inline int device_sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int v = cached[dev & 63].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    cached[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

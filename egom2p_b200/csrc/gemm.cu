@@ -541,16 +541,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-static int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
-  }
-  return cached;
-}
+static int sm_count() { return device_sm_count(); }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_t ldb, uint16_t* c_bf16, float* c_f32,
@@ -578,15 +569,8 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   p.out_bf16 = c_bf16 != nullptr;
   p.out_f32 = c_f32 != nullptr;
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
-    if (e != cudaSuccess) {
-      set_error("gemm: cudaFuncSetAttribute(%d B smem): %s", S::kTotal, cudaGetErrorString(e));
-      return EGOM2P_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};   // one flag set per template instantiation
+  if ((rc = ensure_dyn_smem(kern, S::kTotal, attr_done, "gemm"))) return rc;
   const int sms = sm_count();
   const int k_blocks = (p.K + BK - 1) / BK;
   // split-K: only for fp32 accumulate/plain outputs, when the output tiles cannot fill the machine and K is long
@@ -629,7 +613,7 @@ template <int EPI>
 static int dispatch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_t ldb, int a_mn, int b_mn,
                          uint16_t* c_bf16, float* c_f32, int64_t ldc, const GemmParams& p, cudaStream_t stream) {
   // BN = 256 halves B re-reads per tile; BN = 128 gives better wave quantisation on small problems.
-  const int sms = 148;
+  const int sms = sm_count();
   const int64_t tiles256 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + 255) / 256);
   const bool use256 = (EPI != EPI_STORE) || (p.N >= 256 && (tiles256 >= 2 * sms || !c_bf16));
 #define EGO_GEMM_CASE(BN_, AM, BMJ) return launch_gemm<BN_, AM, BMJ, EPI>(A, B, lda, ldb, c_bf16, c_f32, ldc, p, stream)

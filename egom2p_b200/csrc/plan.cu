@@ -145,7 +145,48 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(PlanParams p) {
   }
 }
 
+// Rows of each modality in the compacted decoder sequence: CTA m scans mod_mask (B * budget int16) for mod_id[m] and writes
+// the matching flat row indices, ascending, into rows[m * cap ..] and their number into counts[m] -- the boolean
+// row-select y[decoder_mod_mask == id] (egom2p_model.py:633) for all modalities in one launch and without a
+// device -> host round trip per modality.
+struct RowsParams {
+  const int16_t* mod_mask;
+  int64_t total;
+  int64_t cap;
+  int32_t mod_id[EGOM2P_MAX_MODS];
+  int64_t* rows;
+  int32_t* counts;
+};
+__global__ void __launch_bounds__(kPlanThreads) plan_rows_kernel(RowsParams p) {
+  __shared__ int s_warp[33];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int16_t id = (int16_t)p.mod_id[m];
+  int64_t* out = p.rows + (int64_t)m * p.cap;
+  int running = 0;
+  for (int64_t base = 0; base < p.total; base += kPlanThreads) {
+    const int64_t i = base + tid;
+    const int v = (i < p.total && p.mod_mask[i] == id) ? 1 : 0;
+    int total;
+    const int pos = running + block_excl_scan(v, s_warp, &total);
+    running += total;
+    if (v) out[pos] = i;
+  }
+  if (tid == 0) p.counts[m] = running;
+}
+
 }  // namespace egom2p
+
+extern "C" int egom2p_plan_rows(const int16_t* mod_mask, int64_t total, const int32_t* mod_ids, int32_t n_mods, int64_t cap,
+                                int64_t* rows, int32_t* counts, void* stream) {
+  using namespace egom2p;
+  EGO_REQUIRE(mod_mask && mod_ids && rows && counts && total > 0 && cap >= total, "plan_rows: bad argument");
+  EGO_REQUIRE(n_mods >= 1 && n_mods <= EGOM2P_MAX_MODS, "plan_rows: n_mods out of range");
+  RowsParams p;
+  p.mod_mask = mod_mask; p.total = total; p.cap = cap; p.rows = rows; p.counts = counts;
+  for (int m = 0; m < n_mods; ++m) p.mod_id[m] = mod_ids[m];
+  plan_rows_kernel<<<n_mods, kPlanThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("plan_rows");
+}
 
 extern "C" int egom2p_index_plan(const egom2p_plan_desc* desc, int32_t* keep_idx, int32_t* keep_mod, int32_t* keep_pos,
                                  uint8_t* pad, int16_t* mod_mask, int32_t* n_valid, int64_t* target_ids,

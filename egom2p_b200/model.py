@@ -112,7 +112,7 @@ class DecoderBlock(nn.Module):
 class _Geom:
     """Shapes + key-range tables of one forward (device tensors, no host syncs)."""
     __slots__ = ("B", "N", "M", "H", "D", "enc_lo", "enc_hi", "dec_lo", "dec_hi", "x_lo", "x_hi", "eps", "m_enc", "m_dec", "m_x",
-                 "ctx_users", "dctx_acc")
+                 "ctx_users", "dctx_acc", "epoch_ref")
 
     def build_meta(self, dev, encoder: bool = True):
         """Range metadata per attention kind, once per forward (shared by all layers, heads, fwd and bwd)."""
@@ -121,6 +121,15 @@ class _Geom:
         if self.M > 0:
             self.m_dec = ops.attn_ranges(self.B, self.M, self.M, self.dec_lo, self.dec_hi, device=dev)
             self.m_x = ops.attn_ranges(self.B, self.M, self.N, self.x_lo, self.x_hi, device=dev)
+
+
+def _check_epoch(ref, seen):
+    """The bf16 operand buffers are re-cast IN PLACE after every optimizer step (EgoM2P._refresh_operands); a backward that
+    runs after such a refresh of a forward made before it would silently use the new weights in its dgrad GEMMs. The
+    reference raises a saved-tensor version error in that situation; so does this."""
+    if ref[0] != seen:
+        raise RuntimeError("egom2p_b200: the bf16 weight operands saved by this forward were refreshed (weights changed and "
+                           "another forward ran) before its backward; run backward before the next forward of updated weights")
 
 
 def _zeros(n, dev):
@@ -143,14 +152,18 @@ def _split_w13_grad(dw13, F):
 def _with_bf16(dx, dxb):
     """Hands the bf16 copy of a residual-stream gradient (written by the LayerNorm backward that produced it, for 1/3 of the
     traffic of a separate cast pass) to the next backward node: autograd passes the same tensor object on, attributes included."""
-    dx._egom2p_bf16 = dxb
+    dx._egom2p_bf16 = (dxb, dx._version, dx.data_ptr())
     return dx
 
 
 def _bf16_of(dx):
-    dxb = getattr(dx, "_egom2p_bf16", None)
-    if dxb is not None and dxb.shape == dx.shape and dxb.device == dx.device and dxb.dtype == bf16:
-        return dxb
+    hit = getattr(dx, "_egom2p_bf16", None)
+    if hit is not None:
+        dxb, ver, ptr = hit
+        # an in-place accumulation into dx (a second consumer of the residual stream, a hook) bumps its version: the copy is
+        # stale then and is rebuilt from the fp32 gradient
+        if ver == dx._version and ptr == dx.data_ptr() and dxb.shape == dx.shape and dxb.device == dx.device and dxb.dtype == bf16:
+            return dxb
     return ops.cast_bf16(dx)
 
 
@@ -207,12 +220,14 @@ class _EncoderBlockFn(torch.autograd.Function):
         x1, sa = _self_attn_fwd(x, n1w, wqkv, wproj, geom.B, geom.N, geom.H, geom.m_enc, geom.eps)
         x2, sm = _mlp_fwd(x1, n2w, w13, w2, geom.eps)
         ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
+        ctx.op_epoch = geom.epoch_ref[0]
         ctx.save_for_backward(x, n1w, n2w, x1, *sa, *sm)
         return x2
 
     @staticmethod
     def backward(ctx, dx2):
         _GRAD_GEN[0] += 1
+        _check_epoch(ctx.geom.epoch_ref, ctx.op_epoch)
         x, n1w, n2w, x1, *rest = ctx.saved_tensors
         sa, sm = rest[:6], rest[6:]
         wqkv, wproj, w13, w2 = ctx.wb
@@ -242,6 +257,7 @@ class _DecoderBlockFn(torch.autograd.Function):
         y2 = ops.linear_fwd(o2, wxproj, addend=y1, out_dtype=f32)
         y3, sm = _mlp_fwd(y2, n2w, w13, w2, g.eps)
         ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
+        ctx.op_epoch = geom.epoch_ref[0]
         ctx.ctx_key = context.data_ptr()
         g.ctx_users += 1
         ctx.save_for_backward(y, context, n1w, qnw, cnw, n2w, y1, y2, meanq, rstdq, hq, q, meanc, rstdc, hc, kv, o2, lse2,
@@ -251,6 +267,7 @@ class _DecoderBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy3):
         _GRAD_GEN[0] += 1
+        _check_epoch(ctx.geom.epoch_ref, ctx.op_epoch)
         (y, context, n1w, qnw, cnw, n2w, y1, y2, meanq, rstdq, hq, q, meanc, rstdc, hc, kv, o2, lse2, *rest) = ctx.saved_tensors
         sa, sm = rest[:6], rest[6:]
         wqkv, wsproj, wq, wkv, wxproj, w13, w2 = ctx.wb
@@ -297,16 +314,18 @@ class _ContextFn(torch.autograd.Function):
     """context = decoder_proj_context(encoder_norm(x)) + encoder_emb -- egom2p_model.py:499,722."""
 
     @staticmethod
-    def forward(ctx, x, enc_emb, norm_w, proj_w, proj_b, wb, eps):
+    def forward(ctx, x, enc_emb, norm_w, proj_w, proj_b, wb, eps, epoch_ref):
         h, _, mean, rstd = ops.layernorm_fwd(x, norm_w, eps)
         context = ops.linear_fwd(h, wb, bias=proj_b, addend=enc_emb, out_dtype=f32)
         ctx.wb = wb
+        ctx.epoch_ref, ctx.op_epoch = epoch_ref, epoch_ref[0]
         ctx.save_for_backward(x, norm_w, mean, rstd, h)
         return context
 
     @staticmethod
     def backward(ctx, dctx):
         _GRAD_GEN[0] += 1
+        _check_epoch(ctx.epoch_ref, ctx.op_epoch)
         x, norm_w, mean, rstd, h = ctx.saved_tensors
         dctx = dctx.contiguous()
         dcb = _bf16_of(dctx)
@@ -315,7 +334,7 @@ class _ContextFn(torch.autograd.Function):
         dh = ops.linear_dgrad(dcb, ctx.wb)
         dnw = _zeros(norm_w.numel(), x.device)
         dx, dxb = ops.layernorm_bwd(dh, x, norm_w, mean, rstd, d_weight=dnw, want_bf16=True)
-        return _with_bf16(dx, dxb), dctx, dnw, dw, db, None, None
+        return _with_bf16(dx, dxb), dctx, dnw, dw, db, None, None, None
 
 
 class _EmbedFn(torch.autograd.Function):
@@ -368,7 +387,8 @@ class _HeadLossFn(torch.autograd.Function):
     CHUNK = 8192
 
     @staticmethod
-    def forward(ctx, y, norm_w, rows, targets, wbs, eps, *head_w):
+    def forward(ctx, y, norm_w, rows, targets, wbs, eps, epoch_ref, *head_w):
+        ctx.epoch_ref, ctx.op_epoch = epoch_ref, epoch_ref[0]
         yn, _, mean, rstd = ops.layernorm_fwd(y, norm_w, eps)
         losses, lses, yms = [], [], []
         for idx, tgt, wb in zip(rows, targets, wbs):
@@ -387,6 +407,7 @@ class _HeadLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *dlosses):
         _GRAD_GEN[0] += 1
+        _check_epoch(ctx.epoch_ref, ctx.op_epoch)
         y, norm_w, mean, rstd = ctx.saved_tensors
         dev = y.device
         D = y.shape[1]
@@ -413,7 +434,7 @@ class _HeadLossFn(torch.autograd.Function):
             dws.append(dw)
         dnw = _zeros(D, dev)
         dy, dyb = ops.layernorm_bwd(dyn, y, norm_w, mean, rstd, d_weight=dnw, want_bf16=True)
-        return (_with_bf16(dy, dyb), dnw, None, None, None, None, *dws)
+        return (_with_bf16(dy, dyb), dnw, None, None, None, None, None, *dws)
 
 
 # =============================================================================================== the module
@@ -471,6 +492,12 @@ class EgoM2P(nn.Module):
         for emb in decoder_embeddings.values():
             emb.init(dim_tokens=dim, init_std=self.init_std)
         self.decoder_embeddings = nn.ModuleDict(decoder_embeddings)
+        for side in (self.encoder_embeddings, self.decoder_embeddings):
+            for mod, emb in side.items():
+                if isinstance(getattr(emb, "pos_emb", None), nn.Parameter):
+                    # the fused embed backward emits gradients for the token tables, mask token and modality embeddings only
+                    raise NotImplementedError(f"egom2p_b200: adapter '{mod}' has a learnable pos_emb (sincos_pos_emb=False); "
+                                              "the fused path supports the fixed sin-cos tables ego-b uses")
         if share_modality_embeddings:
             self.share_modality_embeddings()
 
@@ -485,6 +512,8 @@ class EgoM2P(nn.Module):
         self.init_weights()
         self._wcache: Dict[Any, tuple] = {}
         self._wplan = None
+        self._epoch = [0]   # bumped by every in-place refresh of the bf16 operands (see _check_epoch)
+        self.static_target_rows: Optional[Dict[str, int]] = None   # {modality: valid target rows in the batch}, see forward
 
     # ------------------------------------------------------------------ construction helpers (reference :179-249)
     def share_modality_embeddings(self):
@@ -583,6 +612,7 @@ class EgoM2P(nn.Module):
                     items += [(p.detach(), e[3], 32, i) for i, p in enumerate(e[4])]
             self._wplan = (sig, ops.CastPlan(items))
         self._wplan[1].run()
+        self._epoch[0] += 1
         for k, e in live.items():
             self._wcache[k] = (e[0], tuple(p._version for p in e[4]), _GRAD_GEN[0], e[3], e[4])
 
@@ -613,21 +643,32 @@ class EgoM2P(nn.Module):
 
     @staticmethod
     def _prefix_ranges(mask: Optional[torch.Tensor], B: int, rows: int, keys: int, dev):
-        """(B,1,keys) or (B,rows,keys) bool mask (True = masked) -> per-row [lo, hi) key ranges. The masks this path
-        meets are contiguous per row; anything else would need a dense-mask kernel and raises."""
+        """(B,1,keys) / (B,keys) key-padding mask or (B,rows,keys) mask (bool, True = masked) -> per-row [lo, hi) key
+        ranges, int32 (B, rows). The masks this path meets are one contiguous run per row. The reduction
+        runs on the mask's OWN shape (a key-padding mask costs O(B * keys), not O(B * rows * keys)) and nothing is read
+        back: a non-contiguous row trips a device-side assertion (torch._assert_async) instead of a host sync."""
         if mask is None:
             return None, None
-        m = mask.to(dev).expand(B, rows, keys) if mask.dim() == 3 else mask.to(dev)[:, None, :].expand(B, rows, keys)
-        valid = ~m
-        cnt = valid.sum(-1)
-        ar = torch.arange(keys, device=dev)
-        first = torch.where(valid, ar, keys).amin(-1)
-        last = torch.where(valid, ar, -1).amax(-1) + 1
-        if bool(((last - first).clamp(min=0) != cnt).any()):
-            raise NotImplementedError("egom2p_b200 attention supports one contiguous key range per query row")
-        lo = torch.where(cnt > 0, first, 0).to(torch.int32).contiguous()
-        hi = torch.where(cnt > 0, last, 0).to(torch.int32).contiguous()
-        return lo, hi
+        m = mask.to(dev)
+        if m.dim() == 2:
+            m = m[:, None, :]
+        if m.dtype != torch.bool:
+            m = m != 0
+        if m.shape[0] != B:
+            m = m.expand(B, *m.shape[1:])
+        r = m.shape[1]                     # 1 for a key-padding mask
+        valid = (~m).to(torch.uint8)       # (B, r, keys), one byte per entry
+        cnt = valid.sum(-1, dtype=torch.int32)
+        first = valid.argmax(-1).to(torch.int32)                      # first valid key (0 when the row has none)
+        last = keys - valid.flip(-1).argmax(-1).to(torch.int32)       # one past the last valid key
+        torch._assert_async(((last - first == cnt) | (cnt == 0)).all(),
+                            "egom2p_b200 attention supports one contiguous key range per query row")
+        zero = torch.zeros_like(cnt)
+        lo = torch.where(cnt > 0, first, zero)
+        hi = torch.where(cnt > 0, last, zero)
+        if r != rows:
+            lo, hi = lo.expand(B, rows), hi.expand(B, rows)
+        return lo.contiguous(), hi.contiguous()
 
     def forward_encoder(self, x: torch.Tensor, encoder_mask: torch.Tensor) -> torch.Tensor:
         B, N, D = x.shape
@@ -686,6 +727,7 @@ class EgoM2P(nn.Module):
         g.enc_lo = g.enc_hi = g.dec_lo = g.dec_hi = g.x_lo = g.x_hi = None
         g.m_enc = g.m_dec = g.m_x = None
         g.ctx_users, g.dctx_acc = 0, None   # decoder blocks of this forward that read `context` / their running gradient
+        g.epoch_ref = self._epoch
         return g
 
     # ------------------------------------------------------------------ the training step (reference :683-734)
@@ -749,7 +791,8 @@ class EgoM2P(nn.Module):
             x = _EncoderBlockFn.apply(x, blk.norm1.weight, blk.attn.qkv.weight, blk.attn.proj.weight, blk.norm2.weight,
                                       blk.mlp.fc1.weight, blk.mlp.fc2.weight, blk.mlp.fc3.weight, self._enc_weights(i), g)
         context = _ContextFn.apply(x, enc_emb, self.encoder_norm.weight, self.decoder_proj_context.weight,
-                                   self.decoder_proj_context.bias, self._bf16("ctx", self.decoder_proj_context.weight), self.eps)
+                                   self.decoder_proj_context.bias, self._bf16("ctx", self.decoder_proj_context.weight), self.eps,
+                                   self._epoch)
         # ---- decoder
         for i, blk in enumerate(self.decoder):
             y = self._dec_block(i, blk, y, context, g)
@@ -758,18 +801,26 @@ class EgoM2P(nn.Module):
             yn = self.decoder_norm(y).reshape(B, M, D)
             return {m: self.decoder_embeddings[m].forward_logits(yn) for m in dec_mods}
 
-        # ---- heads + loss: rows of each modality (one small D2H-free nonzero per modality; counts sync like the reference)
-        mod_flat = dp.mod_mask.reshape(-1)
+        # ---- heads + loss: row lists of all modalities from ONE launch; their lengths cross to the host in one copy (the
+        # reference's boolean row-select syncs once per modality, egom2p_model.py:633). With `static_target_rows` set
+        # (CUDA-graph capture, egom2p_b200/graphed.py) the lengths are taken from the host and asserted on the device.
         tgt_flat = dp.target_ids.reshape(-1)
+        row_tab, counts = ops.plan_rows(dp.mod_mask, [ids_of(m) for m in dec_mods])
+        if self.static_target_rows is not None:
+            n_rows = [int(self.static_target_rows[m]) for m in dec_mods]
+            torch._assert_async((counts == torch.tensor(n_rows, dtype=torch.int32, device=dev)).all(),
+                                "egom2p_b200: static_target_rows does not match this batch")
+        else:
+            n_rows = counts.tolist()
         rows, targets, wbs, heads = [], [], [], []
-        for m in dec_mods:
-            idx = torch.nonzero(mod_flat == ids_of(m)).reshape(-1)
+        for i, m in enumerate(dec_mods):
+            idx = row_tab[i, :n_rows[i]]
             rows.append(idx)
             targets.append(tgt_flat.index_select(0, idx))
             w = self.decoder_embeddings[m].to_logits.weight
             heads.append(w)
             wbs.append(self._bf16(("head", m), w))
-        per_mod = _HeadLossFn.apply(y, self.decoder_norm.weight, rows, targets, wbs, self.eps, *heads)
+        per_mod = _HeadLossFn.apply(y, self.decoder_norm.weight, rows, targets, wbs, self.eps, self._epoch, *heads)
         mod_loss = {}
         for m, l in zip(dec_mods, per_mod):
             if loss_type == "weighted_mod" and rows[dec_mods.index(m)].numel():

@@ -17,6 +17,14 @@ def _s() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _req_current(t: torch.Tensor):
+    """Kernels are launched on the CURRENT device's current stream: a tensor living on another device would be addressed
+    from the wrong context. Checked where tensors enter the library (`_req`)."""
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"egom2p_b200: tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}; "
+                           "wrap the call in torch.cuda.device(tensor.device)")
+
+
 class KernelTimer:
     """Optional per-family CUDA-event timing (bench.py's roofline line). When active, wrappers bracket their launches
     with events on the current stream and record algorithmic work; `summary()` synchronises once at the end."""
@@ -71,6 +79,7 @@ def _req(t: torch.Tensor, dtype, name: str):
         raise RuntimeError(f"egom2p_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
     if t.dtype != dtype:
         raise TypeError(f"egom2p_b200: {name} must be {dtype}, got {t.dtype}")
+    _req_current(t)
     return t
 
 
@@ -120,6 +129,20 @@ def index_plan(masks: Sequence[torch.Tensor], mod_ids: Sequence[int], budget: in
                                      _p(pl.mod_mask), _p(pl.n_valid), _p(pl.target_ids), _p(pl.key_lo), _p(pl.key_hi),
                                      _s()), "index_plan")
     return pl
+
+
+def plan_rows(mod_mask: torch.Tensor, mod_ids: Sequence[int]):
+    """Flat row indices of each modality id in `mod_mask` (any shape, int16): returns (rows (n_mods, total) int64 -- only the
+    first counts[m] entries of row m are defined --, counts (n_mods,) int32), both on the device."""
+    lib = _lib.load()
+    _req(mod_mask, torch.int16, "mod_mask")
+    flat = mod_mask.reshape(-1).contiguous()
+    total, n = flat.numel(), len(mod_ids)
+    rows = torch.empty(n, total, dtype=torch.int64, device=flat.device)
+    counts = torch.empty(n, dtype=torch.int32, device=flat.device)
+    ids = (C.c_int32 * n)(*[int(i) for i in mod_ids])
+    _lib.check(lib.egom2p_plan_rows(_p(flat), total, ids, n, total, _p(rows), _p(counts), _s()), "plan_rows")
+    return rows, counts
 
 
 # ----------------------------------------------------------------------------------------------- embedding

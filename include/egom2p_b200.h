@@ -58,6 +58,12 @@ int egom2p_index_plan(const egom2p_plan_desc* desc, int32_t* keep_idx, int32_t* 
                       uint8_t* pad, int16_t* mod_mask, int32_t* n_valid, int64_t* target_ids, int32_t* key_lo,
                       int32_t* key_hi, void* stream);
 
+/* Row lists of the vocabulary heads: for each of n_mods modality ids (host array), the flat indices i (ascending) with
+ * mod_mask[i] == id, written to rows + m * cap (int64, cap >= total), and their number to counts[m] (device int32).
+ * Replaces the per-modality boolean row-select y[decoder_mod_mask == id] (egom2p/models/egom2p_model.py:633). */
+int egom2p_plan_rows(const int16_t* mod_mask, int64_t total, const int32_t* mod_ids, int32_t n_mods, int64_t cap,
+                     int64_t* rows, int32_t* counts, void* stream);
+
 typedef struct {
   int32_t n_mods;
   int32_t dim;

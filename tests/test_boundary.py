@@ -95,3 +95,42 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, sym), sym
     assert _lib.load().egom2p_abi_version() == 1
     assert _lib.load().egom2p_attn_lse_stride(2048) == 2048 and _lib.load().egom2p_attn_lse_stride(20) == 128
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/egom2p"), reason="the reference tree exists in the authoring container only")
+def test_register_into_reference_overrides_registry():
+    """INTEGRATION.md's hook: after register_into_reference() the reference's own create_model (the call get_model makes,
+    run_training_egom2p.py:381-387) builds the B200 module under the unchanged names, with REFERENCE adapter objects, and a
+    reference state_dict loads strictly into it."""
+    from _ref_import import import_reference
+    import_reference()
+    from egom2p.data.modality_info import MODALITY_INFO as REF_MI
+    from egom2p.utils.timm.model_builder import create_model as ref_create
+    e.register_into_reference()
+    mods = ["tok_cam", "tok_gaze"]
+    model = ref_create("egom2p_tiny_6e_6d_swiglu_nobias",
+                       encoder_embeddings={m: REF_MI[m]["encoder_embedding"]() for m in mods},
+                       decoder_embeddings={m: REF_MI[m]["decoder_embedding"]() for m in mods},
+                       modality_info={m: REF_MI[m] for m in mods}, num_register_tokens=0)
+    assert type(model).__module__ == "egom2p_b200.model" and len(model.encoder) == 6
+    assert type(model.encoder_embeddings["tok_cam"]).__module__.startswith("egom2p.models")   # reference adapters, duck-typed
+    ours = e.create_model("egom2p_tiny_6e_6d_swiglu_nobias",
+                          encoder_embeddings={m: MI[m]["encoder_embedding"]() for m in mods},
+                          decoder_embeddings={m: MI[m]["decoder_embedding"]() for m in mods},
+                          modality_info={m: MI[m] for m in mods}, num_register_tokens=0)
+    assert list(ours.state_dict().keys()) == list(model.state_dict().keys())
+    model.load_state_dict(ours.state_dict(), strict=True)
+    causal = ref_create("egom2p_base_12e_12d_swiglu_nobias_causal",
+                        encoder_embeddings={m: REF_MI[m]["encoder_embedding"]() for m in mods},
+                        decoder_embeddings={m: REF_MI[m]["decoder_embedding"]() for m in mods},
+                        modality_info={m: REF_MI[m] for m in mods}, num_register_tokens=0)
+    assert causal.decoder_causal_mask is True
+
+
+def test_learnable_pos_emb_is_rejected():
+    from egom2p_b200 import adapters as A
+    with pytest.raises(NotImplementedError, match="pos_emb"):
+        e.create_model("egom2p_tiny_6e_6d_swiglu_nobias",
+                       encoder_embeddings={"tok_cam": A.GazeCamTokenEncoderEmbedding(sincos_pos_emb=False)},
+                       decoder_embeddings={"tok_cam": A.GazeCamTokenDecoderEmbedding()},
+                       modality_info={"tok_cam": MI["tok_cam"]}, num_register_tokens=0)

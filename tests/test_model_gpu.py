@@ -32,7 +32,8 @@ def build_model(cfg, tie=True):
         info[m] = {"id": inf["id"], "vocab_size": inf["vocab"], "type": inf["type"], "max_tokens": inf["len"]}
     return EgoM2P(enc, dec, info, dim=cfg["dim"], encoder_depth=cfg["enc_depth"], decoder_depth=cfg["dec_depth"],
                   num_heads=cfg["heads"], mlp_ratio=4, qkv_bias=False, proj_bias=False, mlp_bias=False,
-                  norm_layer=partial(LayerNorm, eps=1e-6, bias=False), act_layer=torch.nn.SiLU, gated_mlp=True)
+                  norm_layer=partial(LayerNorm, eps=1e-6, bias=False), act_layer=torch.nn.SiLU, gated_mlp=True,
+                  decoder_causal_mask=cfg.get("causal", False), decoder_sep_mask=cfg.get("sep", True))
 
 
 def to_cuda(md):
@@ -135,3 +136,71 @@ def test_c1_tiny_fm_config(golden_dir):
     for n, p in model.named_parameters():
         got = 0.0 if p.grad is None else p.grad.double().norm().item()
         assert abs(got - norms[n]) <= 3e-2 * norms[n] + 1e-7, (n, got, norms[n])
+
+
+def test_step_weighted_mod_loss():
+    """loss_type='weighted_mod' (egom2p_model.py:581-612): per-modality CE rescaled by ln 256 / ln V; empty modalities stay 0."""
+    cfg = synth.make_cfg(192, 3, 2, 2, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"], video_vocab=512, video_thw=(5, 4, 4))
+    md = synth.make_batch(cfg, B=3, seed=12,
+                          n_in={"tok_cam": [5, 0, 30], "tok_depth": [30, 10, 0], "tok_gaze": [4, 0, 30], "tok_rgb": [25, 40, 4]},
+                          n_tgt={"tok_cam": [10, 30, 0], "tok_depth": [20, 0, 40], "tok_gaze": [0, 0, 0], "tok_rgb": [15, 18, 8]})
+    check_case(cfg, md, 64, 48, seed=8, shuffle_seed=2, loss_type="weighted_mod")
+
+
+def test_step_causal_decoder_variant():
+    """decoder_causal_mask=True (the *_causal registry entries, egom2p_model.py:1029-1051): key range = causal AND own
+    modality segment. Valid rows match the oracle's dense triu mask; pad rows are don't-care."""
+    cfg = synth.make_cfg(192, 3, 2, 2, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"], video_vocab=512, video_thw=(5, 4, 4))
+    cfg["causal"] = True
+    md = synth.make_batch(cfg, B=2, seed=14,
+                          n_in={"tok_cam": [5, 30], "tok_depth": [30, 10], "tok_gaze": [4, 3], "tok_rgb": [25, 40]},
+                          n_tgt={"tok_cam": [10, 30], "tok_depth": [20, 0], "tok_gaze": [3, 7], "tok_rgb": [15, 18]})
+    check_case(cfg, md, 64, 48, seed=10, shuffle_seed=5)
+
+
+def test_prefix_ranges_match_brute_force_and_do_not_scale_with_rows():
+    """Sampler-facing mask -> range conversion (forward_encoder / forward_decoder): equals a brute-force scan for key-padding
+    (B,1,N) and dense (B,M,N) masks, and a (B,1,N) mask at the c5 size (B = 64, N = 9387) costs O(B * N) memory."""
+    from egom2p_b200.model import EgoM2P
+    g = torch.Generator().manual_seed(0)
+    B, M, N = 3, 37, 101
+    lens = torch.tensor([0, 17, 101])
+    kp = (torch.arange(N)[None, :] >= lens[:, None])[:, None, :].cuda()                 # (B,1,N), True = masked
+    lo, hi = EgoM2P._prefix_ranges(kp, B, M, N, kp.device)
+    assert lo.shape == (B, M) and lo.dtype == torch.int32
+    assert torch.equal(lo.cpu(), torch.zeros(B, M, dtype=torch.int32)) and torch.equal(hi.cpu(), lens[:, None].expand(B, M).int())
+    a = torch.randint(0, N, (B, M), generator=g)
+    w = torch.randint(0, 40, (B, M), generator=g)
+    ar = torch.arange(N)[None, None, :]
+    dense = ~((ar >= a[..., None]) & (ar < (a + w)[..., None]))                         # one run per row, some rows empty
+    lo, hi = EgoM2P._prefix_ranges(dense.cuda(), B, M, N, kp.device)
+    want_hi = torch.minimum(a + w, torch.tensor(N))
+    empty = want_hi <= a
+    assert torch.equal(lo.cpu()[~empty], a.int()[~empty]) and torch.equal(hi.cpu()[~empty], want_hi.int()[~empty])
+    assert bool((hi.cpu()[empty] == lo.cpu()[empty]).all())
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    big = torch.zeros(64, 1, 9387, dtype=torch.bool, device="cuda")
+    lo, hi = EgoM2P._prefix_ranges(big, 64, 9387, 9387, big.device)
+    torch.cuda.synchronize()
+    assert torch.cuda.max_memory_allocated() - base < 64 * 9387 * 4 * 4    # lo / hi (B, rows) int32 dominate: < 10 MB
+    assert int(hi[0, 0]) == 9387
+
+
+def test_backward_after_operand_refresh_raises():
+    """A backward that runs after the bf16 weight operands were refreshed in place for a later forward must not silently use
+    the new weights (the reference raises a saved-tensor version error there)."""
+    cfg = synth.make_cfg(192, 3, 1, 1, ["tok_cam", "tok_gaze"])
+    model = build_model(cfg).cuda()
+    model.load_state_dict(synth.make_state_dict(cfg, 1), strict=True)
+    md = to_cuda(synth.make_batch(cfg, B=1, seed=2, n_in={"tok_cam": [9], "tok_gaze": [7]}, n_tgt={"tok_cam": [8], "tok_gaze": [6]}))
+    loss_a, _ = model(md, 16, 16)
+    loss_b, _ = model(md, 16, 16)
+    loss_b.backward()                       # weights "about to change": the next forward re-casts every operand in place
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(1e-3)
+    loss_c, _ = model(md, 16, 16)
+    with pytest.raises(RuntimeError, match="refreshed"):
+        loss_a.backward()
