@@ -287,6 +287,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--regime", default="dense", choices=["dense", "reference-masks"],
                     help="dense: SURVEY 8(d) headline synthetic regime; reference-masks: ragged masks drawn by the reference's UnifiedMasking")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: egom2p_b200.optim.FusedAdamW (multi-tensor clip + AdamW); torch: clip_grad_norm_ + torch.optim.AdamW(fused=True)")
+    ap.add_argument("--no-batch4", action="store_true", help="skip the extra b = 4 per GPU measurement (the reference's own batch size; N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the b = 1 full-size parity gate against the reference's fp32 outputs")
     ap.add_argument("--no-reference-gpu", action="store_true",
@@ -320,8 +323,12 @@ def main():
                                                         broadcast_buffers=False, gradient_as_bucket_view=True)
     decay = [p for n, p in model.named_parameters() if not ("norm" in n or n.endswith(".bias"))]
     no_decay = [p for n, p in model.named_parameters() if ("norm" in n or n.endswith(".bias"))]
-    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}],
-                            lr=1e-4, betas=(0.9, 0.95), eps=1e-8, fused=True)
+    groups = [{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}]
+    if args.optimizer == "fused":   # the device-side tail of this repo: grad-norm + AdamW in two launches over all 245 tensors
+        from egom2p_b200.optim import FusedAdamW
+        opt = FusedAdamW(groups, lr=1e-4, betas=(0.9, 0.95), eps=1e-8)
+    else:
+        opt = torch.optim.AdamW(groups, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, fused=True)
     params = list(model.parameters())
 
     # a fresh batch for every warm-up and timed step (seed = 1234 + rank * 1000 + step): nothing to memorise
@@ -338,7 +345,10 @@ def main():
     def step(md):
         loss, mod_loss = net(md, N_ENC, N_DEC, loss_type="mod")
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        if args.optimizer == "fused":
+            opt.clip_grad_norm_(1.0)
+        else:
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -384,6 +394,33 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     last_loss = e2e_step(0)
 
+    # ---- the reference's own per-GPU batch (4): eager, and as one CUDA graph per step (egom2p_b200/graphed.py)
+    batch4 = None
+    if world == 1 and not args.no_batch4 and args.regime == "dense" and args.optimizer == "fused":
+        from egom2p_b200.graphed import GraphedTrainStep
+        from egom2p_b200.optim import FusedAdamW
+        nb4 = args.steps * 2
+        b4 = [{m: {k: v.to(dev) for k, v in d.items()} for m, d in make_batch(4, 777 + s, pin=False).items()} for s in range(nb4 + 1)]
+        for i in range(3):
+            step(b4[i])
+        l0 = _lib.launch_count()
+        ms4 = timed(lambda i: step(b4[i]), nb4)
+        l4 = (_lib.launch_count() - l0) / nb4
+        opt.zero_grad(set_to_none=True)
+        opt4 = FusedAdamW(groups, lr=1e-4, betas=(0.9, 0.95), eps=1e-8)
+        runner = GraphedTrainStep(model, opt4, b4[nb4], N_ENC, N_DEC, clip_grad=1.0)
+        for i in range(3):
+            runner(b4[i])
+        ms4g = timed(lambda i: runner(b4[i]), nb4)
+        model.static_target_rows = None
+        model.fixed_decoder_order = None
+        del runner, opt4
+        mk4 = lambda ms_: {"ms_per_step": ms_ / nb4, "tokens_per_s": 4 * NOMINAL_TOKENS / (ms_ / nb4 / 1e3),
+                           "mfu_vs_2250_spec": 4 * FLOP_PER_SAMPLE_STEP / (ms_ / nb4 / 1e3) / 1e12 / 2250.0}
+        batch4 = {"what": "same training step at b = 4 per GPU (the reference's batch_size), dense regime, steps = %d" % nb4,
+                  "eager": dict(mk4(ms4), launches_per_step=l4),
+                  "cuda_graph": dict(mk4(ms4g), launches_per_step=1, note="whole step (fwd + bwd + clip + AdamW) replayed as one graph")}
+
     # ---- per-kernel-family breakdown of one extra step (CUDA events around each C-ABI launch)
     with ops.KernelTimer() as kt:
         step(dev_batches[0])
@@ -417,6 +454,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": md_bytes(host_batches[0]), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "parity": parity,
+            "batch4": batch4,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all nn.Linear fwd/dgrad/wgrad)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
@@ -441,7 +479,7 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "baseline"))
             import ref_gpu
             if ref_gpu.available():
-                del opt, params, net, model, dev_batches
+                del opt, params, net, model, dev_batches, groups, decay, no_decay
                 import gc
                 gc.collect()
                 torch.cuda.empty_cache()

@@ -51,13 +51,11 @@ SIGNATURES = {
     "egom2p_attn_bwd_scratch_bytes": [i32, i32, i32],
     "egom2p_attn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, f32, vp, vp, vp, vp,
                         i64, i64, i64, vp],
-    "egom2p_swiglu_fwd": [vp, i64, i32, vp, vp],
-    "egom2p_swiglu_bwd": [vp, vp, i64, i32, vp, vp],
     "egom2p_cast_f32_to_bf16": [vp, vp, i64, vp],
     "egom2p_cast_f32_to_bf16_multi": [vp, i32, i64, vp],
     "egom2p_add_f32": [vp, vp, i64, vp, vp, vp],
-    "egom2p_adamw_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp],
-    "egom2p_sumsq_f32": [vp, i64, vp, vp],
+    "egom2p_sumsq_multi": [vp, i32, i64, vp, vp],
+    "egom2p_adamw_multi": [vp, i32, i64, f32, f32, f32, vp, vp, f32, vp],
     "egom2p_colsum_f32": [vp, i64, i32, vp, vp],
     "egom2p_gather_rows_bf16": [vp, vp, i64, i32, vp, vp],
     "egom2p_scatter_rows_f32": [vp, vp, i64, i32, vp, vp],

@@ -1,6 +1,6 @@
-// HBM-bound elementwise kernels on the path: SwiGLU gate (egom2p_utils.py:167-169), casts, residual add,
-// fused AdamW (torch.optim.AdamW semantics) and sum-of-squares for the global grad-norm clip.
-// All are grid-stride, 16-byte vectorised, grid = 148 SMs x 8 CTAs.
+// HBM-bound elementwise kernels on the path: casts, residual add, row gather / scatter, and the optimizer tail
+// (multi-tensor sum of squares for the global grad-norm clip + multi-tensor AdamW, torch.optim.AdamW semantics).
+// 16-byte vectorised; grid-stride with grid = 148 SMs x 8 CTAs, or one block per chunk of a device-resident item table.
 #include "common.cuh"
 
 namespace egom2p {
@@ -25,52 +25,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 r;
   r.x = pack_bf16(f[0], f[1]); r.y = pack_bf16(f[2], f[3]); r.z = pack_bf16(f[4], f[5]); r.w = pack_bf16(f[6], f[7]);
   return r;
-}
-
-__global__ void __launch_bounds__(kEwThreads) swiglu_fwd_kernel(const uint16_t* __restrict__ ab, int64_t rows, int hidden,
-                                                                uint16_t* __restrict__ g) {
-  const int H8 = hidden >> 3;
-  const int64_t n = rows * H8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / H8;
-    const int c = (int)(i - r * H8);
-    const uint4 ra = reinterpret_cast<const uint4*>(ab + r * 2 * hidden)[c];
-    const uint4 rb = reinterpret_cast<const uint4*>(ab + r * 2 * hidden + hidden)[c];
-    float a[8], b[8], o[8];
-    unpack8(ra, a);
-    unpack8(rb, b);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      o[k] = a[k] / (1.f + __expf(-a[k])) * b[k];
-    }
-    reinterpret_cast<uint4*>(g + r * hidden)[c] = pack8(o);
-  }
-}
-
-__global__ void __launch_bounds__(kEwThreads) swiglu_bwd_kernel(const uint16_t* __restrict__ ab, const uint16_t* __restrict__ dg,
-                                                                int64_t rows, int hidden, uint16_t* __restrict__ dab) {
-  const int H8 = hidden >> 3;
-  const int64_t n = rows * H8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / H8;
-    const int c = (int)(i - r * H8);
-    const uint4 ra = reinterpret_cast<const uint4*>(ab + r * 2 * hidden)[c];
-    const uint4 rb = reinterpret_cast<const uint4*>(ab + r * 2 * hidden + hidden)[c];
-    const uint4 rg = reinterpret_cast<const uint4*>(dg + r * hidden)[c];
-    float a[8], b[8], d[8], da[8], db[8];
-    unpack8(ra, a);
-    unpack8(rb, b);
-    unpack8(rg, d);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float sg = 1.f / (1.f + __expf(-a[k]));
-      const float s = a[k] * sg;
-      db[k] = d[k] * s;
-      da[k] = d[k] * b[k] * (sg * (1.f + a[k] * (1.f - sg)));
-    }
-    reinterpret_cast<uint4*>(dab + r * 2 * hidden)[c] = pack8(da);
-    reinterpret_cast<uint4*>(dab + r * 2 * hidden + hidden)[c] = pack8(db);
-  }
 }
 
 __global__ void __launch_bounds__(kEwThreads) cast_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n) {
@@ -151,27 +105,53 @@ __global__ void __launch_bounds__(kEwThreads) add_kernel(const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(kEwThreads) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                           float* __restrict__ v, int64_t n, float lr, float b1, float b2,
-                                                           float eps, float wd, float bc1, float bc2_sqrt,
-                                                           const float* __restrict__ gscale) {
-  const float gs = gscale ? *gscale : 1.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gs;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi;
+// ---- optimizer tail (the reference: NativeScalerWithGradNormCount.__call__, egom2p/utils/native_scaler.py:27-47 =
+// clip_grad_norm_ + optimizer.step over 245 tensors; AdamW from egom2p/utils/optim_factory.py:206-226). Two launches over
+// a device-resident table of all tensors: sum of squares of every gradient -> one scalar; then AdamW with the clip
+// coefficient min(1, max_norm / (norm + 1e-6)) folded into the gradient read, so the gradients are never rewritten.
+// A block = one chunk of kOptChunk elements of one tensor, found by bisection over the items' first chunks.
+struct OptItem {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+  int64_t first_chunk;
+  float lr, wd;
+};
+static_assert(sizeof(OptItem) == 56, "OptItem layout is part of the C ABI (egom2p_opt_item)");
+constexpr int kOptChunk = 8192;
+
+__device__ __forceinline__ OptItem find_item(const OptItem* __restrict__ items, int n_items, OptItem* sh) {
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {  // last item with first_chunk <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].first_chunk <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    *sh = items[lo];
   }
+  __syncthreads();
+  return *sh;
 }
 
-__global__ void __launch_bounds__(kEwThreads) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(kEwThreads) sumsq_multi_kernel(const OptItem* __restrict__ items, int n_items, float* __restrict__ out) {
+  __shared__ OptItem sh_it;
+  const OptItem it = find_item(items, n_items, &sh_it);
+  const int64_t e0 = ((int64_t)blockIdx.x - it.first_chunk) * kOptChunk;
+  const int ne = (int)min((int64_t)kOptChunk, it.n - e0);
+  const float* g = it.g + e0;
   float s = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i] * x[i];
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const int n4 = ne >> 2;
+    for (int i = threadIdx.x; i < n4; i += kEwThreads) {
+      const float4 x = reinterpret_cast<const float4*>(g)[i];
+      s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < ne; i += kEwThreads) s += g[i] * g[i];
+  } else {
+    for (int i = threadIdx.x; i < ne; i += kEwThreads) s += g[i] * g[i];
+  }
   s = warp_sum(s);
   __shared__ float sh[kEwThreads / 32];
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -182,6 +162,59 @@ __global__ void __launch_bounds__(kEwThreads) sumsq_kernel(const float* __restri
     if (threadIdx.x == 0) atomicAdd(out, t);
   }
 }
+
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float lr, float wd, float b1, float b2, float eps,
+                                          float step_size, float inv_bc2_sqrt) {
+  p *= 1.f - lr * wd;
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+  p -= step_size * (m / denom);
+}
+
+// step_dev holds the number of steps taken BEFORE this one (incremented by step_inc_kernel afterwards), so that the whole
+// tail is capturable in a CUDA graph: no host-side scalar changes from step to step.
+__global__ void __launch_bounds__(kEwThreads) adamw_multi_kernel(const OptItem* __restrict__ items, int n_items, float b1, float b2,
+                                                                 float eps, const int32_t* __restrict__ step_dev,
+                                                                 const float* __restrict__ sumsq, float max_norm) {
+  __shared__ OptItem sh_it;
+  const OptItem it = find_item(items, n_items, &sh_it);
+  const float t = (float)(*step_dev + 1);
+  const float bc1 = 1.f - powf(b1, t), inv_bc2_sqrt = rsqrtf(1.f - powf(b2, t));
+  float gs = 1.f;
+  if (sumsq) gs = fminf(1.f, max_norm / (sqrtf(*sumsq) + 1e-6f));   // torch.nn.utils.clip_grad_norm_
+  const float step_size = it.lr / bc1;
+  const int64_t e0 = ((int64_t)blockIdx.x - it.first_chunk) * kOptChunk;
+  const int ne = (int)min((int64_t)kOptChunk, it.n - e0);
+  float* p = it.p + e0;
+  const float* g = it.g + e0;
+  float* m = it.m + e0;
+  float* v = it.v + e0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  int done = 0;
+  if (aligned) {
+    const int n4 = ne >> 2;
+    for (int i = threadIdx.x; i < n4; i += kEwThreads) {
+      float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+      const float4 gv = reinterpret_cast<const float4*>(g)[i];
+      adamw_one(pv.x, gv.x * gs, mv.x, vv.x, it.lr, it.wd, b1, b2, eps, step_size, inv_bc2_sqrt);
+      adamw_one(pv.y, gv.y * gs, mv.y, vv.y, it.lr, it.wd, b1, b2, eps, step_size, inv_bc2_sqrt);
+      adamw_one(pv.z, gv.z * gs, mv.z, vv.z, it.lr, it.wd, b1, b2, eps, step_size, inv_bc2_sqrt);
+      adamw_one(pv.w, gv.w * gs, mv.w, vv.w, it.lr, it.wd, b1, b2, eps, step_size, inv_bc2_sqrt);
+      reinterpret_cast<float4*>(p)[i] = pv;
+      reinterpret_cast<float4*>(m)[i] = mv;
+      reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    done = n4 << 2;
+  }
+  for (int i = done + threadIdx.x; i < ne; i += kEwThreads) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adamw_one(pi, g[i] * gs, mi, vi, it.lr, it.wd, b1, b2, eps, step_size, inv_bc2_sqrt);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+__global__ void step_inc_kernel(int32_t* step) { *step += 1; }
 
 // out[c] += sum_r x[r, c]; each CTA reduces a 64-row slab, threads own columns (coalesced), one atomic per column.
 __global__ void __launch_bounds__(kEwThreads) colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ out) {
@@ -234,18 +267,6 @@ extern "C" int egom2p_scatter_rows_f32(const float* src, const int64_t* idx, int
   return check_launch("scatter_rows_f32");
 }
 
-extern "C" int egom2p_swiglu_fwd(const uint16_t* ab, int64_t rows, int32_t hidden, uint16_t* g, void* stream) {
-  using namespace egom2p;
-  EGO_REQUIRE(ab && g && rows > 0 && hidden > 0 && hidden % 8 == 0, "swiglu_fwd: bad argument (hidden %% 8 == 0 required)");
-  swiglu_fwd_kernel<<<ew_grid(rows * (hidden / 8)), kEwThreads, 0, (cudaStream_t)stream>>>(ab, rows, hidden, g);
-  return check_launch("swiglu_fwd");
-}
-extern "C" int egom2p_swiglu_bwd(const uint16_t* ab, const uint16_t* dg, int64_t rows, int32_t hidden, uint16_t* dab, void* stream) {
-  using namespace egom2p;
-  EGO_REQUIRE(ab && dg && dab && rows > 0 && hidden > 0 && hidden % 8 == 0, "swiglu_bwd: bad argument");
-  swiglu_bwd_kernel<<<ew_grid(rows * (hidden / 8)), kEwThreads, 0, (cudaStream_t)stream>>>(ab, dg, rows, hidden, dab);
-  return check_launch("swiglu_bwd");
-}
 extern "C" int egom2p_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
   using namespace egom2p;
   EGO_REQUIRE(src && dst && n > 0, "cast_f32_to_bf16: bad argument");
@@ -265,20 +286,22 @@ extern "C" int egom2p_add_f32(const float* a, const float* b, int64_t n, float* 
   add_kernel<<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)stream>>>(a, b, n, out, out_bf16);
   return check_launch("add_f32");
 }
-extern "C" int egom2p_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                                 float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                                 const float* grad_scale, void* stream) {
+extern "C" int egom2p_sumsq_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float* sumsq, void* stream) {
   using namespace egom2p;
-  EGO_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adamw_step: bad argument");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  adamw_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                                   weight_decay, bc1, bc2s, grad_scale);
-  return check_launch("adamw_step");
+  EGO_REQUIRE(items_dev && sumsq && n_items > 0 && n_chunks > 0 && n_chunks < (int64_t)INT32_MAX, "sumsq_multi: bad argument");
+  cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(float), (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("sumsq_multi: memset: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
+  sumsq_multi_kernel<<<(unsigned)n_chunks, kEwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const OptItem*>(items_dev), n_items, sumsq);
+  return check_launch("sumsq_multi");
 }
-extern "C" int egom2p_sumsq_f32(const float* x, int64_t n, float* sumsq, void* stream) {
+extern "C" int egom2p_adamw_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float beta1, float beta2, float eps,
+                                  int32_t* step_dev, const float* sumsq, float max_norm, void* stream) {
   using namespace egom2p;
-  EGO_REQUIRE(x && sumsq && n > 0, "sumsq_f32: bad argument");
-  sumsq_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(x, n, sumsq);
-  return check_launch("sumsq_f32");
+  EGO_REQUIRE(items_dev && step_dev && n_items > 0 && n_chunks > 0 && n_chunks < (int64_t)INT32_MAX, "adamw_multi: bad argument");
+  adamw_multi_kernel<<<(unsigned)n_chunks, kEwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const OptItem*>(items_dev), n_items,
+                                                                                 beta1, beta2, eps, step_dev, sumsq, max_norm);
+  int rc = check_launch("adamw_multi");
+  if (rc) return rc;
+  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  return check_launch("adamw_multi step");
 }

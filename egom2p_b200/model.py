@@ -514,6 +514,7 @@ class EgoM2P(nn.Module):
         self._wplan = None
         self._epoch = [0]   # bumped by every in-place refresh of the bf16 operands (see _check_epoch)
         self.static_target_rows: Optional[Dict[str, int]] = None   # {modality: valid target rows in the batch}, see forward
+        self.fixed_decoder_order: Optional[List[str]] = None
 
     # ------------------------------------------------------------------ construction helpers (reference :179-249)
     def share_modality_embeddings(self):
@@ -761,6 +762,8 @@ class EgoM2P(nn.Module):
         ep = ops.index_plan([mod_dict[m]["input_mask"] for m in enc_mods], [ids_of(m) for m in enc_mods], num_encoder_tokens)
         # decoder modality order is shuffled exactly like the reference (random.sample over the dict items, :312)
         dec_order = [m for m, _ in random.sample([(m, None) for m in dec_mods], len(dec_mods))]
+        if self.fixed_decoder_order is not None:   # CUDA-graph replay: the order drawn at capture time (the loss is order-invariant, A7)
+            dec_order = [m for m in self.fixed_decoder_order if m in dec_mods]
         for m in dec_order:
             if self.modality_info[m]["type"] in ("seq", "seq_emb", "seq_token"):
                 raise NotImplementedError("sequence (teacher-forced) decoder modalities are not part of the mod4 path")

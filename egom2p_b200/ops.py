@@ -358,24 +358,6 @@ def attn_bwd(q, k, v, o, do, lse, B, H, Mq, Nk, dq, dk, dv, key_lo=None, key_hi=
 
 
 # ----------------------------------------------------------------------------------------------- elementwise
-def swiglu_fwd(ab: torch.Tensor):
-    lib = _lib.load()
-    rows, h2 = ab.shape
-    g = torch.empty(rows, h2 // 2, dtype=bf16, device=ab.device)
-    with _timed("swiglu", rows * h2 * 3.0, "byte"):
-        _lib.check(lib.egom2p_swiglu_fwd(_p(ab), rows, h2 // 2, _p(g), _s()), "swiglu_fwd")
-    return g
-
-
-def swiglu_bwd(ab: torch.Tensor, dg: torch.Tensor):
-    lib = _lib.load()
-    rows, h2 = ab.shape
-    dab = torch.empty_like(ab)
-    with _timed("swiglu", rows * h2 * 5.0, "byte"):
-        _lib.check(lib.egom2p_swiglu_bwd(_p(ab), _p(dg), rows, h2 // 2, _p(dab), _s()), "swiglu_bwd")
-    return dab
-
-
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None):
     lib = _lib.load()
     _req(src, f32, "src")
@@ -426,17 +408,6 @@ def add_f32(a, b, want_f32=True, want_bf16=False):
     outb = torch.empty(a.shape, dtype=bf16, device=a.device) if want_bf16 else None
     _lib.check(lib.egom2p_add_f32(_p(a), _p(b), a.numel(), _p(out), _p(outb), _s()), "add_f32")
     return out, outb
-
-
-def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=None):
-    lib = _lib.load()
-    _lib.check(lib.egom2p_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, wd, step, _p(grad_scale),
-                                     _s()), "adamw_step")
-
-
-def sumsq(x, out):
-    lib = _lib.load()
-    _lib.check(lib.egom2p_sumsq_f32(_p(x), x.numel(), _p(out), _s()), "sumsq_f32")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor):

@@ -167,9 +167,6 @@ int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, con
 /* ------------------------------------------------------------------------------------------------
  * Elementwise helpers on the path.
  * ------------------------------------------------------------------------------------------------ */
-/* g = silu(a) * b with ab = [a | b] (rows, 2*hidden) bf16 -> g (rows, hidden) bf16 (egom2p_utils.py:167-169). */
-int egom2p_swiglu_fwd(const uint16_t* ab, int64_t rows, int32_t hidden, uint16_t* g, void* stream);
-int egom2p_swiglu_bwd(const uint16_t* ab, const uint16_t* dg, int64_t rows, int32_t hidden, uint16_t* dab, void* stream);
 int egom2p_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
 /* One launch for a list of casts: the per-step refresh of the bf16 GEMM operands from the fp32 master weights
  * (the reference gets this from torch.autocast's weight cache, run_training_egom2p.py:716). Item i casts a contiguous
@@ -187,19 +184,32 @@ typedef struct {
 int egom2p_cast_f32_to_bf16_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, void* stream);
 /* out = a + b (fp32), optional bf16 copy. */
 int egom2p_add_f32(const float* a, const float* b, int64_t n, float* out, uint16_t* out_bf16, void* stream);
-/* Fused AdamW over one flat fp32 tensor (torch.optim.AdamW semantics; egom2p/utils/optim_factory.py:206-226),
- * grad pre-scaled by *grad_scale (device scalar, e.g. the clip coefficient; NULL = 1). */
-int egom2p_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                      float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* grad_scale,
-                      void* stream);
+/* Optimizer tail over ALL trainable tensors in two launches (the reference: clip_grad_norm_ + AdamW.step driven by
+ * NativeScalerWithGradNormCount.__call__, egom2p/utils/native_scaler.py:27-47; AdamW groups from
+ * egom2p/utils/optim_factory.py:206-226). The item table lives in device memory; first_chunk = running sum of
+ * ceil(n / 8192) over the items before i, n_chunks = the total.
+ *   egom2p_sumsq_multi: *sumsq = sum over all items of sum(g^2) (zeroed inside, fp32 atomics).
+ *   egom2p_adamw_multi: torch.optim.AdamW update of every item with its own lr / weight decay; the gradient is read as
+ *     g * min(1, max_norm / (sqrt(*sumsq) + 1e-6)) when sumsq != NULL (clip folded in: gradients are not rewritten);
+ *     bias corrections use *step_dev + 1, and *step_dev is incremented afterwards (CUDA-graph capturable). */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  int64_t first_chunk;
+  float lr, weight_decay;
+} egom2p_opt_item;
+int egom2p_sumsq_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float* sumsq, void* stream);
+int egom2p_adamw_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float beta1, float beta2, float eps,
+                       int32_t* step_dev, const float* sumsq, float max_norm, void* stream);
 /* out[c] += sum_r x[r, c] -- bias gradient of decoder_proj_context (egom2p_model.py:157,722). */
 int egom2p_colsum_f32(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
 /* dst[i, :] = src[idx[i], :] (bf16) and dst[idx[i], :] = src[i, :] (fp32): compaction of the rows of one modality for
  * its vocabulary head, replacing the boolean row-select y[decoder_mod_mask == id] (egom2p_model.py:633). */
 int egom2p_gather_rows_bf16(const uint16_t* src, const int64_t* idx, int64_t n, int32_t cols, uint16_t* dst, void* stream);
 int egom2p_scatter_rows_f32(const float* src, const int64_t* idx, int64_t n, int32_t cols, float* dst, void* stream);
-/* sumsq[0] += sum(x^2) (fp32 atomics) -- building block of clip_grad_norm_ (egom2p/utils/native_scaler.py:29-33). */
-int egom2p_sumsq_f32(const float* x, int64_t n, float* sumsq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -149,34 +149,45 @@ def test_layernorm_fwd_bwd(ops, rows, dim):
     torch.testing.assert_close(dx2.cpu(), xr.grad, rtol=5e-2, atol=2e-2)
 
 
-def test_swiglu_cast_add_adamw(ops):
+def test_cast(ops):
     gen = torch.Generator().manual_seed(1)
-    ab = (torch.randn(300, 2 * 512, generator=gen) * 2).bfloat16()
-    dg = torch.randn(300, 512, generator=gen).bfloat16()
-    a, b = ab[:, :512].float().requires_grad_(), ab[:, 512:].float().requires_grad_()
-    g = torch.nn.functional.silu(a) * b
-    g.backward(dg.float())
-    got = ops.swiglu_fwd(dev(ab))
-    torch.testing.assert_close(got.cpu().float(), g.detach(), rtol=1e-2, atol=1e-2)
-    dab = ops.swiglu_bwd(dev(ab), dev(dg)).cpu().float()
-    torch.testing.assert_close(dab[:, :512], a.grad, rtol=2e-2, atol=2e-2)
-    torch.testing.assert_close(dab[:, 512:], b.grad, rtol=2e-2, atol=2e-2)
     x = torch.randn(1001, generator=gen)
     assert torch.equal(ops.cast_bf16(dev(x)).cpu(), x.bfloat16())
-    # AdamW vs torch.optim.AdamW, 3 steps
-    p0 = torch.randn(5000, generator=gen)
-    pr = p0.clone().requires_grad_()
-    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
-    p, m, v = dev(p0.clone()), torch.zeros(5000, device="cuda"), torch.zeros(5000, device="cuda")
-    for step in range(1, 4):
-        gr = torch.randn(5000, generator=gen)
-        pr.grad = gr.clone()
-        opt.step()
-        ops.adamw_step(p, dev(gr), m, v, 1e-3, 0.9, 0.95, 1e-8, 0.05, step)
-    torch.testing.assert_close(p.cpu(), pr.detach(), rtol=1e-5, atol=1e-6)
-    ss = torch.zeros(1, device="cuda")
-    ops.sumsq(dev(p0), ss)
-    torch.testing.assert_close(ss.cpu()[0], (p0.double() ** 2).sum().float(), rtol=1e-4, atol=0)
+
+
+def test_fused_adamw_and_clip_match_torch():
+    """Optimizer tail (egom2p/utils/native_scaler.py:27-47): multi-tensor grad-norm + AdamW with the clip folded in, against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW over two parameter groups, odd sizes, 4 steps, a changing lr and a
+    parameter without gradient."""
+    from egom2p_b200.optim import FusedAdamW, FusedScalerWithGradNormCount
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(5000,), (33, 7), (1, 1, 768), (8193,), (64, 129), (3,)]
+    p_ref = [torch.randn(s, generator=gen).requires_grad_() for s in shapes]
+    p_new = [torch.nn.Parameter(dev(p.detach().clone())) for p in p_ref]
+    frozen_ref, frozen_new = torch.randn(10).requires_grad_(), torch.nn.Parameter(torch.randn(10, device="cuda"))
+    kw = dict(lr=1e-3, betas=(0.9, 0.95), eps=1e-8)
+    groups = lambda ps, fr: [{"params": ps[:3] + [fr], "weight_decay": 0.05}, {"params": ps[3:], "weight_decay": 0.0}]
+    o_ref = torch.optim.AdamW(groups(p_ref, frozen_ref), **kw)
+    o_new = FusedAdamW(groups(p_new, frozen_new), **kw)
+    scaler = FusedScalerWithGradNormCount(enabled=False)
+    for step in range(4):
+        for g_ref, g_new in zip(o_ref.param_groups, o_new.param_groups):
+            g_ref["lr"] = g_new["lr"] = 1e-3 * (1 + step)            # the reference scheduler rewrites param_group["lr"] each step
+        scale = 50.0 if step % 2 else 0.01                             # norm above and below max_norm = 1
+        grads = [torch.randn(s, generator=gen) * scale for s in shapes]
+        for p, g in zip(p_ref, grads):
+            p.grad = g.clone()
+        n_ref = torch.nn.utils.clip_grad_norm_(p_ref + [frozen_ref], 1.0)
+        o_ref.step()
+        # the same gradients through backward() on the GPU side
+        loss = sum((p * dev(g)).sum() for p, g in zip(p_new, grads))
+        n_new = scaler(loss, o_new, clip_grad=1.0, parameters=p_new)
+        o_new.zero_grad(set_to_none=True)
+        torch.testing.assert_close(n_new.cpu(), n_ref, rtol=1e-5, atol=0)
+    for a, b in zip(p_new, p_ref):
+        torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=2e-5, atol=2e-6)
+    assert int(o_new._step_dev.item()) == 4
+    assert frozen_new.grad is None and not o_new.state[frozen_new]
 
 
 # ------------------------------------------------------------------------------------------ tcgen05 GEMM

@@ -133,3 +133,47 @@ def test_loop_body_under_autocast_and_scaler():
     for a, b in zip(plain, amp):
         assert abs(a - b) <= 2e-4 * abs(a), (plain, amp)
     assert plain[-1] < 0.95 * plain[0]
+
+
+def test_graphed_step_matches_eager():
+    """egom2p_b200.graphed.GraphedTrainStep (whole-step CUDA graph: forward + backward + clip + FusedAdamW) reproduces the
+    eager step: same losses and the same weights after 3 steps on 3 different batches with equal target counts."""
+    import copy
+    from egom2p_b200.graphed import GraphedTrainStep
+    from egom2p_b200.optim import FusedAdamW
+    from test_model_gpu import build_model, to_cuda
+    cfg = synth.make_cfg(192, 3, 2, 2, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"], video_vocab=512, video_thw=(5, 4, 4))
+    n_in = {"tok_cam": [5, 30], "tok_depth": [30, 10], "tok_gaze": [4, 3], "tok_rgb": [25, 21]}
+    n_tg = {"tok_cam": [10, 3], "tok_depth": [20, 7], "tok_gaze": [3, 7], "tok_rgb": [15, 18]}
+    batches = [to_cuda(synth.make_batch(cfg, B=2, seed=30 + i, n_in=n_in, n_tgt=n_tg)) for i in range(4)]
+    sd = synth.make_state_dict(cfg, 4)
+    models = []
+    for _ in range(2):
+        m = build_model(cfg).cuda()
+        m.load_state_dict(sd, strict=True)
+        models.append(m)
+    eager, graphed = models
+    mk = lambda m: FusedAdamW([{"params": [p for n, p in m.named_parameters() if "norm" not in n], "weight_decay": 0.05},
+                               {"params": [p for n, p in m.named_parameters() if "norm" in n], "weight_decay": 0.0}],
+                              lr=3e-3, betas=(0.9, 0.95), eps=1e-8)
+    o_e, o_g = mk(eager), mk(graphed)
+    runner = GraphedTrainStep(graphed, o_g, batches[3], 64, 48, clip_grad=1.0)
+    eager.fixed_decoder_order = list(graphed.fixed_decoder_order)
+    for i in range(3):
+        if i == 2:   # a scheduler changes the learning rate between steps
+            for g1, g2 in zip(o_e.param_groups, o_g.param_groups):
+                g1["lr"] = g2["lr"] = 1e-3
+            runner.set_hyper()
+        loss_e, _ = eager(batches[i], 64, 48)
+        loss_e.backward()
+        n_e = o_e.clip_grad_norm_(1.0)
+        o_e.step()
+        o_e.zero_grad(set_to_none=True)
+        loss_g = runner(batches[i])
+        torch.cuda.synchronize()
+        assert abs(loss_e.item() - loss_g.item()) <= 2e-4 * abs(loss_e.item()), (i, loss_e.item(), loss_g.item())
+        assert abs(n_e.item() - runner.grad_norm.item()) <= 2e-3 * n_e.item()
+    assert int(o_g._step_dev.item()) == 3
+    worst = max(((a.detach() - b.detach()).abs().max() / (b.detach().abs().max() + 1e-12)).item()
+                for a, b in zip(graphed.parameters(), eager.parameters()))
+    assert worst < 2e-3, worst   # dQ accumulates through fp32 atomics: the two runs are not bit-identical
