@@ -11,6 +11,20 @@
 // tcgen05.mma issuer + TMEM owner.
 //
 //   S = Q K^T (TMEM) -> online softmax -> P (bf16, swizzled smem) -> O_blk = P V (TMEM) -> O += in registers
+//
+// Two softmax paths, chosen per CTA:
+//   * bound path (default): every row uses the FIXED reference m_r = |q_r| * max_k |k| * scale * log2(e) >= every score of the
+//     row (Cauchy-Schwarz; max_k |k|^2 per (batch, head) comes from a small pre-pass over K). P = 2^(s - m_r) <= 1 can never
+//     overflow, so there is no running maximum, no exchange between the two column halves of a row, no rescaling of O, and
+//     the row sum comes out of the PV MMA itself (a constant tile of ones widens V to N = 80: column 64 of O is sum_k P).
+//     The result is mathematically identical; P is merely scaled by 2^(max_r - m_r) >= 2^(-2 m_r) per row, which bf16 / fp32
+//     represent exactly as well as long as m_r <= 60 (P stays a normal number). Per score that leaves one FFMA, one
+//     MUFU.EX2, half a pack and 1/8 of a shared store: the kernel runs at the MUFU rate instead of the latency of the
+//     max-exchange chain.
+//   * online path (any row of the tile with m_r > 60, or no pre-pass scratch given): the running-maximum softmax with lazy
+//     rescaling described above.
+#include <cstdlib>
+
 #include "attn_common.cuh"
 
 namespace egom2p {
@@ -58,6 +72,36 @@ __global__ void __launch_bounds__(128) attn_blocks_kernel(int B, int S, RangeMet
   if (lane == 0) { m.blk_lo[blk] = lo; m.blk_hi[blk] = hi; m.blk_lo_max[blk] = lo_max; m.blk_hi_min[blk] = hi_min; }
 }
 
+// max over the keys of one (batch, head) of |k|^2, as the int bits of a non-negative float (atomicMax), for the bound path.
+// One warp handles 4 keys per step (8 lanes x 16 bytes = one 64-element key row).
+__global__ void __launch_bounds__(256) attn_kmax_kernel(const uint16_t* __restrict__ K, int64_t ldk, int Nk, int H,
+                                                        int* __restrict__ kmax2) {
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 256 + warp * 32;
+  float best = 0.f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int key = k0 + it * 4 + (lane >> 3);
+    float s = 0.f;
+    if (key < Nk) {
+      const uint4 w = *reinterpret_cast<const uint4*>(K + ((int64_t)b * Nk + key) * ldk + h * kD + (lane & 7) * 8);
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[u]));
+        s = fmaf(f.x, f.x, fmaf(f.y, f.y, s));
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    best = fmaxf(best, s);
+  }
+  best = warp_max(best);
+  if (lane == 0) atomicMax(kmax2 + b * H + h, __float_as_int(best));
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 struct AttnFwdParams {
   int B, H, Mq, Nk, S;
@@ -65,19 +109,26 @@ struct AttnFwdParams {
   uint16_t* O;
   int64_t ldo;
   float* lse2;  // (B, H, S), log2 domain: m + log2(l)
+  const float* kmax2;  // (B, H) max_k |k|^2 (bound path), or NULL (online path only)
 };
+constexpr float kBoundLimit = 60.f;  // log2 units: rows with |q| max|k| scale log2e above this take the online path
 
-constexpr int kFwdStages = 3;
+constexpr int kFwdStages = 4;
 constexpr float kRescaleThreshold = 8.f;  // log2 units: O / l are rescaled only when the row max grows by > 2^8
 struct FwdSmem {
-  static constexpr int kQ = 0;
+  static constexpr int kQ = 0;                             // staging only: Q moves to TMEM before the first MMA
   static constexpr int kK = kQ + kT * 128;
   static constexpr int kV = kK + kFwdStages * kBlk * 128;
-  static constexpr int kP = kV + kFwdStages * kBlk * 128;  // two P buffers
-  static constexpr int kX = kP + 2 * kT * 128;             // exchange slots: [2 parities][2 halves][128 rows] floats
+  static constexpr int kOnes = kV + kFwdStages * kBlk * 128;  // [64 keys][64 bf16] of 1.0: V's MN group 64..127 (16 columns used)
+  static constexpr int kX = kOnes + kBlk * 128;            // exchange slots: [2 parities][2 halves][128 rows] floats
   static constexpr int kBar = kX + 2 * 2 * kT * 4;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
+// TMEM columns of one CTA (256 allocated; two CTAs per SM share the 512): S fp32 | O fp32 (64 head-dim columns + 16 of
+// the ones group, column 64 = row sum of P) | Q as packed bf16 pairs | two P buffers as packed bf16 pairs.
+constexpr int kPvN = kD + 16;
+constexpr uint32_t cS = 0, cO = 64, cQ = cO + kPvN, cP = cQ + 32;
+static_assert(cP + 2 * 32 <= 256, "attention forward TMEM budget");
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -90,11 +141,27 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {  // one fp32 column of this thread's lane
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 
-// O accumulates in TMEM across the whole key loop (tcgen05.mma accumulate), so the math warps never wait for a PV
-// product inside the loop; they only touch O when a row maximum grows by more than 2^8 ("lazy rescaling": until then P
-// and the running sum stay relative to the stale maximum, which is exact after the final O / l division).
+// Shared-memory bandwidth, not the MUFU, bounded the first version of this kernel (A = Q re-read from smem for every S
+// product, P written to and read back from smem: 82 KB of smem traffic per 64-key block against 128 B / clk). Q and P now
+// live in TMEM as packed bf16 pairs and enter the MMAs as TMEM operands; shared memory only carries K, V and the ones tile.
+// O accumulates in TMEM across the whole key loop (tcgen05.mma accumulate), so the math warps never wait for a PV product
+// inside the loop.
+template <int kPoly>   // kPoly > 0: every kPoly-th exponential of an interior block on the FMA pipes (ex2_poly) instead of the MUFU
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -103,17 +170,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem + FwdSmem::kQ;
   uint8_t* sK = smem + FwdSmem::kK;
   uint8_t* sV = smem + FwdSmem::kV;
-  uint8_t* sP = smem + FwdSmem::kP;
+  uint8_t* sOnes = smem + FwdSmem::kOnes;
   float* sX = reinterpret_cast<float*>(smem + FwdSmem::kX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBar);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
+  uint64_t* q_full = bars;                       // Q tile in smem (TMA)
+  uint64_t* q_tmem = bars + 1;                   // Q copied to TMEM by the math warps, ones tile written
+  uint64_t* kv_full = bars + 2;
   uint64_t* kv_empty = kv_full + kFwdStages;
   uint64_t* s_full = kv_empty + kFwdStages;
   uint64_t* s_free = s_full + 1;
   uint64_t* p_full = s_free + 1;   // [2]
   uint64_t* pv_done = p_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  int* s_slow = reinterpret_cast<int*>(tmem_slot + 1);   // set when some row of the tile exceeds the bound limit
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
@@ -123,16 +192,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == kTmaWarp && lane == 0) {
     mbar_init(q_full, 1);
+    mbar_init(q_tmem, kAttnComputeWarps);
     for (int i = 0; i < kFwdStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
     mbar_init(s_free, kAttnComputeWarps);
     for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], kAttnComputeWarps); mbar_init(&pv_done[i], 1); }
+    *s_slow = p.kmax2 ? 0 : 1;
     fence_mbar_init();
     // the Q tile does not depend on the key range: its load overlaps the range metadata reads and the TMEM allocation
     mbar_expect_tx(q_full, kT * 128);
     tma_load_2d(sQ, &tmQ, q_full, h * kD, b * p.Mq + q0);
   }
-  if (warp == kMmaWarp) tmem_alloc<128>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<256>(tmem_slot);
+  if (warp < kAttnComputeWarps) {   // the ones tile (constant): 512 x 16 bytes over 256 threads
+    const uint4 one4 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = one4;
+    reinterpret_cast<uint4*>(sOnes)[threadIdx.x + 256] = one4;
+  }
   int lo = INT_MAX, hi = INT_MIN;
   float rscale = 0.f;
   if (warp < kAttnComputeWarps && row < p.Mq) {   // the row's range: in flight while the barriers / TMEM are set up
@@ -172,21 +248,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == kMmaWarp) {
     if (nblk > 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kBlk, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kD, 0, 1);
-      const uint32_t tS = tmem_base, tO = tmem_base + 64;
-      const uint64_t dQ0 = umma_desc_kmajor_sw128(smem_u32(sQ));
-      auto issue_s = [&](int st) {  // S = Q K^T, 4 k-steps of 16
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kBlk, 0, 0);    // A = Q (TMEM) x K-major K block
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kPvN, 0, 1);   // A = P (TMEM) x MN-major [V | ones]
+      const uint32_t tS = tmem_base + cS, tO = tmem_base + cO, tQ = tmem_base + cQ, tP = tmem_base + cP;
+      auto issue_s = [&](int st) {  // S = Q K^T, 4 k-steps of 16 (8 TMEM columns of packed pairs each)
         const uint64_t dK0 = umma_desc_kmajor_sw128(smem_u32(sK + st * kBlk * 128));
         if (elect_one()) {
-          umma_bf16_ss(tS, dQ0, dK0, idesc_s, 0u);
 #pragma unroll
-          for (int k = 1; k < 4; ++k) umma_bf16_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tS, tQ + 8 * k, dK0 + 2 * k, idesc_s, k ? 1u : 0u);
           umma_commit(s_full);
         }
         __syncwarp();
       };
-      mbar_wait(q_full, 0);
+      mbar_wait(q_tmem, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       issue_s(0);
@@ -201,12 +275,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         mbar_wait(&p_full[buf], (j >> 1) & 1);
         tc_fence_after();
-        const uint64_t dP0 = umma_desc_kmajor_sw128(smem_u32(sP + buf * kT * 128));
-        const uint64_t dV0 = umma_desc_mnmajor_sw128(smem_u32(sV + st * kBlk * 128), 8192);
+        // V stage = MN group 0 (head-dim columns 0..63); the ones tile = MN group 1, LBO bytes further on (columns 64..79)
+        const uint64_t dV0 = umma_desc_mnmajor_sw128(smem_u32(sV + st * kBlk * 128), (uint32_t)(sOnes - (sV + st * kBlk * 128)));
         if (elect_one()) {
-          umma_bf16_ss(tO, dP0, dV0, idesc_pv, j ? 1u : 0u);
 #pragma unroll
-          for (int k = 1; k < 4; ++k) umma_bf16_ss(tO, dP0 + 2 * k, dV0 + 128 * k, idesc_pv, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tO, tP + buf * 32 + 8 * k, dV0 + 128 * k, idesc_pv, (j | k) ? 1u : 0u);
           umma_commit(&pv_done[buf]);
           umma_commit(&kv_empty[st]);
         }
@@ -215,13 +288,93 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ---------------------------------------------------------------- softmax warps: thread == (query row, column half)
-    const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;
-    const uint32_t t_o = tmem_base + ((uint32_t)(quarter * 32) << 16) + 64 + half * 32;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + cS + half * 32;
+    const uint32_t t_o = t_lane + cO + half * 32;
+    const uint32_t t_p = t_lane + cP + half * 16;   // this thread's 32 keys = 16 packed columns of a P buffer
     float m_used = -INFINITY, l = 0.f;
+    // ---- Q: smem -> TMEM (this thread's row, its half of the head dim = 16 packed columns), row norm for the bound path
+    float m_row = 0.f;
+    if (nblk > 0) {
+      mbar_wait(q_full, 0);
+      float q2 = 0.f;
+      uint32_t qw[16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 w = *reinterpret_cast<const uint4*>(sQ + swz_off(trow, c));
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[u]));
+          q2 = fmaf(f.x, f.x, fmaf(f.y, f.y, q2));
+          if ((c >> 2) == half) qw[(c & 3) * 4 + u] = ww[u];
+        }
+      }
+      tmem_st16(t_lane + cQ + half * 16, qw);
+      if (p.kmax2) {
+        m_row = sqrtf(q2 * p.kmax2[b * p.H + h]) * rscale;   // 0 for uniform (fully masked) and padding rows
+        if (m_row > kBoundLimit) *s_slow = 1;
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      fence_async_smem();                                    // the ones tile -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_tmem);
+    }
+    asm volatile("bar.sync 5, 256;" ::: "memory");            // the eight math warps: s_slow is final
+    const bool fast = *s_slow == 0;
+    if (fast) {
+      for (int j = 0; j < nblk; ++j) {
+        const int buf = j & 1;
+        const int kv0 = lo_cta + j * kBlk + half * 32;
+        mbar_wait(s_full, j & 1);   // also: PV(j-2) has retired (commit order of the single MMA thread): P buffer `buf` is free
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(t_s, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        const float nm = -m_row;
+        uint32_t pk[16];
+        const bool interior = rscale != 0.f && kv0 >= lo && kv0 + 32 <= hi;
+        if (__all_sync(0xffffffffu, interior)) {
+          // every score of the warp's 32 x 32 patch is inside its row's range: a in [-2 m_r, 0]; one exponential in kPoly
+          // goes to the FMA pipes (the MUFU is the busiest unit of this kernel)
+#pragma unroll
+          for (int c2 = 0; c2 < 16; ++c2) {
+            const float a0 = fmaf(__uint_as_float(v[c2 * 2]), rscale, nm), a1 = fmaf(__uint_as_float(v[c2 * 2 + 1]), rscale, nm);
+            const float e0 = (kPoly > 0 && (c2 * 2) % (kPoly > 0 ? kPoly : 1) == 0) ? ex2_poly(a0) : ex2(a0);
+            const float e1 = (kPoly > 0 && (c2 * 2 + 1) % (kPoly > 0 ? kPoly : 1) == 0) ? ex2_poly(a1) : ex2(a1);
+            pk[c2] = pack_bf16(e0, e1);
+          }
+        } else {
+          const float sc = rscale != 0.f ? rscale : 1.f;
+#pragma unroll
+          for (int c2 = 0; c2 < 16; ++c2) {
+            float e[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int c = c2 * 2 + u;
+              const bool ok = (kv0 + c >= lo) && (kv0 + c < hi);
+              const float sv = rscale != 0.f ? __uint_as_float(v[c]) : 0.f;
+              e[u] = ok ? ex2(fmaf(sv, sc, nm)) : 0.f;
+            }
+            pk[c2] = pack_bf16(e[0], e[1]);
+          }
+        }
+        tmem_st16(t_p + buf * 32, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[buf]);
+      }
+      m_used = m_row;
+    } else
     for (int j = 0; j < nblk; ++j) {
       const int buf = j & 1;
       const int kv0 = lo_cta + j * kBlk + half * 32;  // first key of this thread's 32 columns
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1);   // (also covers PV(j-2): P buffer `buf` is free)
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(t_s, v);
@@ -271,20 +424,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const float nm = (m_used == -INFINITY) ? 0.f : -m_used;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      if (j >= 2) mbar_wait(&pv_done[buf], ((j - 2) >> 1) & 1);  // PV(j-2) no longer reads this P buffer
-      uint8_t* pb = sP + buf * kT * 128;
+      uint32_t pk[16];
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float e[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) e[u] = ex2(fmaf(__uint_as_float(v[c8 * 8 + u]), sc, nm));
         sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
-        uint4 pk;
-        pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
-        *reinterpret_cast<uint4*>(pb + swz_off(trow, half * 4 + c8)) = pk;
+        pk[c8 * 4 + 0] = pack_bf16(e[0], e[1]); pk[c8 * 4 + 1] = pack_bf16(e[2], e[3]);
+        pk[c8 * 4 + 2] = pack_bf16(e[4], e[5]); pk[c8 * 4 + 3] = pack_bf16(e[6], e[7]);
       }
       l += (sum0 + sum1) + (sum2 + sum3);
-      fence_async_smem();
+      tmem_st16(t_p + buf * 32, pk);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[buf]);
     }
@@ -299,10 +452,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < 32; ++c) ov[c] = 0u;
     }
-    float* xs = sX + (nblk & 1) * 2 * kT;
-    xs[half * kT + trow] = l;
-    pair_sync(quarter);
-    const float lt = l + xs[(half ^ 1) * kT + trow];
+    float lt;
+    if (fast) {
+      lt = nblk > 0 ? __uint_as_float(tmem_ld1(t_lane + cO + kD)) : 0.f;
+      tmem_ld_wait();
+    } else {
+      float* xs = sX + (nblk & 1) * 2 * kT;
+      xs[half * kT + trow] = l;
+      pair_sync(quarter);
+      lt = l + xs[(half ^ 1) * kT + trow];
+    }
     if (row < p.Mq) {
       const float inv = lt > 0.f ? 1.f / lt : 0.f;
       uint16_t* orow = p.O + ((int64_t)b * p.Mq + row) * p.ldo + h * kD + half * 32;
@@ -322,7 +481,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
@@ -349,7 +508,7 @@ extern "C" int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, 
 
 extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, int32_t B, int32_t H, int32_t Mq,
                                int32_t Nk, int64_t ldq, int64_t ldk, int64_t ldv, const void* meta, uint16_t* O, int64_t ldo,
-                               float* lse, void* stream) {
+                               float* lse, float* kmax_scratch, void* stream) {
   using namespace egom2p;
   EGO_REQUIRE(Q && O && meta && B > 0 && H > 0 && Mq > 0 && Nk >= 0, "attn_fwd: bad argument");
   EGO_REQUIRE(ldo % 8 == 0 && ((uintptr_t)O & 15) == 0, "attn_fwd: O must be 16-byte aligned with ldo %% 8 == 0");
@@ -357,6 +516,7 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
   p.B = B; p.H = H; p.Mq = Mq; p.Nk = Nk; p.S = padS(Mq);
   p.meta = carve_meta(const_cast<void*>(meta), B, Mq);
   p.O = O; p.ldo = ldo; p.lse2 = lse;
+  p.kmax2 = nullptr;
   CUtensorMap tmQ, tmK, tmV;
   int rc = make_tmap_bf16_2d(&tmQ, Q, (uint64_t)B * Mq, (uint64_t)H * kD, ldq, kT, kD);
   if (rc) return rc;
@@ -368,9 +528,25 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
     tmK = tmQ;
     tmV = tmQ;
   }
-  static std::atomic<uint64_t> attr_done{0};
-  if ((rc = ensure_dyn_smem(attn_fwd_kernel, FwdSmem::kTotal, attr_done, "attn_fwd"))) return rc;
+  static const int mode = [] { const char* e = getenv("EGOM2P_ATTN_FWD"); return e ? atoi(e) : 0; }();  // tuning knob: -1 online, 0 bound, n > 0 bound + poly
+  if (kmax_scratch && Nk > 0 && mode >= 0) {   // pre-pass of the bound path: max_k |k|^2 per (batch, head)
+    EGO_REQUIRE(ldk % 8 == 0 && ((uintptr_t)K & 15) == 0, "attn_fwd: K must be 16-byte aligned with ldk %% 8 == 0");
+    cudaError_t e = cudaMemsetAsync(kmax_scratch, 0, (size_t)B * H * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("attn_fwd: memset: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
+    attn_kmax_kernel<<<dim3((Nk + 255) / 256, H, B), 256, 0, (cudaStream_t)stream>>>(K, ldk, Nk, H, reinterpret_cast<int*>(kmax_scratch));
+    if ((rc = check_launch("attn_kmax"))) return rc;
+    p.kmax2 = kmax_scratch;
+  }
   dim3 grid((Mq + kT - 1) / kT, H, B);
-  attn_fwd_kernel<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-  return check_launch("attn_fwd");
+  static std::atomic<uint64_t> attr_done[4];
+  auto launch = [&](auto kern, int slot) -> int {
+    int r = ensure_dyn_smem(kern, FwdSmem::kTotal, attr_done[slot], "attn_fwd");
+    if (r) return r;
+    kern<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    return check_launch("attn_fwd");
+  };
+  if (mode == 3) return launch(attn_fwd_kernel<3>, 3);
+  if (mode == 4) return launch(attn_fwd_kernel<4>, 1);
+  if (mode == 8) return launch(attn_fwd_kernel<8>, 2);
+  return launch(attn_fwd_kernel<0>, 0);
 }

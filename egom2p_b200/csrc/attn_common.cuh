@@ -33,6 +33,14 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.9999280571937561f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 16 bf16 (8 columns of packed pairs), issued by ONE thread.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {  // 16-byte chunk in a [rows][128 B] SW128 tile
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }

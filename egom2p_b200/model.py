@@ -515,6 +515,7 @@ class EgoM2P(nn.Module):
         self._epoch = [0]   # bumped by every in-place refresh of the bf16 operands (see _check_epoch)
         self.static_target_rows: Optional[Dict[str, int]] = None   # {modality: valid target rows in the batch}, see forward
         self.fixed_decoder_order: Optional[List[str]] = None
+        self._static_rows_dev = None
 
     # ------------------------------------------------------------------ construction helpers (reference :179-249)
     def share_modality_embeddings(self):
@@ -811,7 +812,10 @@ class EgoM2P(nn.Module):
         row_tab, counts = ops.plan_rows(dp.mod_mask, [ids_of(m) for m in dec_mods])
         if self.static_target_rows is not None:
             n_rows = [int(self.static_target_rows[m]) for m in dec_mods]
-            torch._assert_async((counts == torch.tensor(n_rows, dtype=torch.int32, device=dev)).all(),
+            key = (tuple(n_rows), dev)
+            if self._static_rows_dev is None or self._static_rows_dev[0] != key:   # built outside graph capture (warm-up)
+                self._static_rows_dev = (key, torch.tensor(n_rows, dtype=torch.int32, device=dev))
+            torch._assert_async((counts == self._static_rows_dev[1]).all(),
                                 "egom2p_b200: static_target_rows does not match this batch")
         else:
             n_rows = counts.tolist()

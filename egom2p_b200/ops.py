@@ -337,10 +337,11 @@ def attn_fwd(q, k, v, B, H, Mq, Nk, key_lo=None, key_hi=None, scale=None, want_l
         meta = attn_ranges(B, Mq, Nk, key_lo, key_hi, scale, device=q.device)
     o = torch.empty(B * Mq, H * 64, dtype=bf16, device=q.device)
     lse = torch.empty(B, H, lse_stride(Mq), dtype=f32, device=q.device) if want_lse else None
+    kmax = torch.empty(B * H, dtype=f32, device=q.device) if Nk > 0 else None   # scratch of the bound-path pre-pass
     with _timed("attn_fwd", 4.0 * B * H * Mq * Nk * 64, "flop"):
         _lib.check(lib.egom2p_attn_fwd(_p(q), _p(k) if Nk > 0 else None, _p(v) if Nk > 0 else None, B, H, Mq, Nk, q.stride(0),
                                        k.stride(0) if Nk > 0 else 0, v.stride(0) if Nk > 0 else 0, _p(meta), _p(o),
-                                       o.stride(0), _p(lse), _s()), "attn_fwd")
+                                       o.stride(0), _p(lse), _p(kmax), _s()), "attn_fwd")
     return o, lse
 
 

@@ -152,10 +152,12 @@ int64_t egom2p_attn_ranges_bytes(int32_t B, int32_t Mq); /* bytes of the range m
  * forward and backward kernels. key_lo / key_hi are (B, Mq) int32 or both NULL. meta: 256-byte aligned. */
 int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, int32_t B, int32_t Mq, int32_t Nk, float scale,
                        void* meta, void* stream);
-/* lse is (B, H, S) fp32 in log2 units (max + log2(sum) of scale*log2e*scores), saved for the backward pass. */
+/* lse is (B, H, S) fp32 in log2 units (reference + log2(sum) of scale*log2e*scores), saved for the backward pass.
+ * kmax_scratch: B*H floats of device scratch for the pre-pass of the bound-path softmax (max_k |k|^2 per batch and head,
+ * see csrc/attn.cu), or NULL to force the online-maximum softmax. */
 int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint16_t* V, int32_t B, int32_t H, int32_t Mq, int32_t Nk,
                     int64_t ldq, int64_t ldk, int64_t ldv, const void* meta, uint16_t* O, int64_t ldo, float* lse,
-                    void* stream);
+                    float* kmax_scratch, void* stream);
 /* Bytes of device scratch egom2p_attn_bwd needs (per-row delta terms + the fp32 dQ accumulator). */
 int64_t egom2p_attn_bwd_scratch_bytes(int32_t B, int32_t H, int32_t Mq);
 /* dQ/dK/dV use the same addressing as Q/K/V with their own row pitches; dO shares O's pitch. */

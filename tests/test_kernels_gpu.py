@@ -281,13 +281,16 @@ def _attn_ref(q, k, v, lo, hi, H):
     return (p @ vh).permute(0, 2, 1, 3).reshape(B, Mq, H * 64), s
 
 
+@pytest.mark.parametrize("gain", [1.0, 3.0])   # 1: |q| max|k| scale log2e ~ 15 -> bound-path softmax; 3: ~ 140 -> online-maximum path
 @pytest.mark.parametrize("B,H,Mq,Nk,mode", [(2, 3, 200, 200, "prefix"), (1, 2, 128, 64, "full"), (2, 4, 300, 517, "prefix"),
                                             (2, 2, 260, 260, "segments"), (1, 1, 20, 24, "prefix"), (1, 12, 2048, 2048, "segments")])
-def test_attention_fwd(ops, B, H, Mq, Nk, mode):
+def test_attention_fwd(ops, B, H, Mq, Nk, mode, gain):
     gen = torch.Generator().manual_seed(Mq * 7 + Nk)
     D = H * 64
-    qkv = torch.randn(B, Mq, 3 * D, generator=gen).bfloat16()
-    kvsrc = qkv if Mq == Nk else torch.randn(B, Nk, 3 * D, generator=gen).bfloat16()
+    qkv = torch.randn(B, Mq, 3 * D, generator=gen)
+    qkv[..., :2 * D] *= gain
+    qkv = qkv.bfloat16()
+    kvsrc = qkv if Mq == Nk else torch.randn(B, Nk, 3 * D, generator=gen).mul_(torch.tensor([gain] * (2 * D) + [1.0] * D)).bfloat16()
     q, k, v = qkv[..., :D], kvsrc[..., D:2 * D], kvsrc[..., 2 * D:]
     if mode == "full":
         lo = torch.zeros(B, Mq, dtype=torch.int32); hi = torch.full((B, Mq), Nk, dtype=torch.int32)
@@ -299,10 +302,16 @@ def test_attention_fwd(ops, B, H, Mq, Nk, mode):
         lo = torch.zeros(B, Mq, dtype=torch.int32); hi = torch.zeros(B, Mq, dtype=torch.int32)
         for a, b_ in zip(bounds[:-1], bounds[1:]):
             lo[:, a:b_] = a; hi[:, a:b_] = b_
-    ref, _ = _attn_ref(q, k, v, lo.long(), hi.long(), H)
+    ref, s_ref = _attn_ref(q, k, v, lo.long(), hi.long(), H)
     qd, kd = dev(qkv).reshape(B * Mq, 3 * D), dev(kvsrc).reshape(B * Nk, 3 * D)
     o, lse = ops.attn_fwd(qd[:, :D], kd[:, D:2 * D], kd[:, 2 * D:], B, H, Mq, Nk, dev(lo), dev(hi))
     torch.testing.assert_close(o.cpu().float().reshape(B, Mq, D), ref.float(), rtol=2e-2, atol=2e-2)
+    # saved statistic (consumed by the backward): log2-sum-exp of the scaled scores over the row's range
+    rows = (hi > lo)
+    lse_ref = torch.logsumexp(s_ref, -1) * 1.4426950408889634       # (B, H, Mq)
+    got = lse.cpu()[:, :, :Mq].double()
+    for b in range(B):
+        torch.testing.assert_close(got[b][:, rows[b]], lse_ref[b][:, rows[b]], rtol=1e-3, atol=2e-2)
 
 
 def test_attention_fwd_no_keys(ops):

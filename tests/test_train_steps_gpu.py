@@ -174,6 +174,10 @@ def test_graphed_step_matches_eager():
         assert abs(loss_e.item() - loss_g.item()) <= 2e-4 * abs(loss_e.item()), (i, loss_e.item(), loss_g.item())
         assert abs(n_e.item() - runner.grad_norm.item()) <= 2e-3 * n_e.item()
     assert int(o_g._step_dev.item()) == 3
-    worst = max(((a.detach() - b.detach()).abs().max() / (b.detach().abs().max() + 1e-12)).item()
-                for a, b in zip(graphed.parameters(), eager.parameters()))
-    assert worst < 2e-3, worst   # dQ accumulates through fp32 atomics: the two runs are not bit-identical
+    # Adam moves every element by about +-lr per step whatever the gradient's size, and dQ accumulates through fp32 atomics
+    # (run-to-run noise in the last bits): elements with a near-zero gradient may step in opposite directions in the two runs.
+    # So: the bulk of the weights agrees closely, and no element is further apart than the steps taken (3e-3 + 3e-3 + 1e-3).
+    lr_sum = 7e-3
+    for a, b in zip(graphed.parameters(), eager.parameters()):
+        d = (a.detach() - b.detach()).abs()
+        assert d.max().item() <= 2.2 * lr_sum and d.mean().item() <= 0.05 * lr_sum, (tuple(a.shape), d.max().item(), d.mean().item())
