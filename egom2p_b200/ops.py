@@ -433,3 +433,37 @@ def scatter_rows_f32(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor):
     if n:
         _lib.check(lib.egom2p_scatter_rows_f32(_p(src), _p(idx), n, cols, _p(dst), _s()), "scatter_rows_f32")
     return dst
+
+
+# ----------------------------------------------------------------------------------------------- generation
+def sample_rows(logits: torch.Tensor, temperature: float, top_p: float = 0.0, top_k: int = 0, u: Optional[torch.Tensor] = None,
+                want_prob: bool = True, want_kept: bool = False):
+    """One token per row of fp32 logits (rows, V) with the reference's temperature / top-k / top-p semantics
+    (generate.py:332-371). u: uniforms in [0, 1) per row (drawn with torch.rand on the current generator if None).
+    Returns (token int64 (rows,), prob fp32 or None, n_kept int32 or None)."""
+    lib = _lib.load()
+    _req(logits, f32, "logits")
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    rows, V = logits.shape
+    if u is None:
+        u = torch.rand(rows, device=logits.device, dtype=f32)
+    _req(u, f32, "u")
+    tok = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    prob = torch.empty(rows, dtype=f32, device=logits.device) if want_prob else None
+    kept = torch.empty(rows, dtype=torch.int32, device=logits.device) if want_kept else None
+    if rows:
+        with _timed("sample", rows * V * 4.0, "byte"):
+            _lib.check(lib.egom2p_sample_rows(_p(logits), logits.stride(0), rows, V, float(temperature), float(top_p), int(top_k),
+                                              _p(u.contiguous()), _p(tok), _p(prob), _p(kept), _s()), "sample_rows")
+    return tok, prob, kept
+
+
+def cfg_combine_bf16(y_uncond: torch.Tensor, y_cond: torch.Tensor, scale: float) -> torch.Tensor:
+    """bf16(y_u + (y_c - y_u) * scale) for fp32 tensors of equal shape (classifier-free guidance before the linear head)."""
+    lib = _lib.load()
+    _req(y_uncond, f32, "y_uncond"); _req(y_cond, f32, "y_cond")
+    assert y_uncond.shape == y_cond.shape and y_uncond.is_contiguous() and y_cond.is_contiguous()
+    out = torch.empty(y_uncond.shape, dtype=bf16, device=y_uncond.device)
+    if out.numel():
+        _lib.check(lib.egom2p_cfg_combine_bf16(_p(y_uncond), _p(y_cond), y_uncond.numel(), float(scale), _p(out), _s()), "cfg_combine_bf16")
+    return out

@@ -213,6 +213,22 @@ int egom2p_colsum_f32(const float* x, int64_t rows, int32_t cols, float* out, vo
 int egom2p_gather_rows_bf16(const uint16_t* src, const int64_t* idx, int64_t n, int32_t cols, uint16_t* dst, void* stream);
 int egom2p_scatter_rows_f32(const float* src, const int64_t* idx, int64_t n, int32_t cols, float* dst, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Generation (guided ROAR / MaskGIT decoding, egom2p/models/generate.py): fused sampling.
+ * ------------------------------------------------------------------------------------------------ */
+/* One token per row from fp32 logits (rows, V), row pitch ld, with the semantics of GenerationSampler.sample_tokens /
+ * top_k_top_p_filtering (egom2p/models/generate.py:332-371): top-k (logits below the k-th largest are removed; 0 = off),
+ * then top-p on softmax(remaining) at temperature 1 (a token is removed when the mass ranked strictly above it exceeds
+ * top_p; 0 = off), then one draw from softmax(kept / temperature) -- here by inverse CDF in ascending token order with the
+ * uniform u[row] in [0, 1); temperature == 0: argmax, prob 1. No sort and no second copy of the logits: threshold search by
+ * nested 2048-bin mass histograms. Outputs: token (rows) int64, prob (rows) fp32 of the drawn token (may be NULL),
+ * n_kept (rows) int32 size of the filtered set (may be NULL). V <= 65536. */
+int egom2p_sample_rows(const float* logits, int64_t ld, int32_t rows, int32_t V, float temperature, float top_p,
+                       int32_t top_k, const float* u, int64_t* token, float* prob, int32_t* n_kept, void* stream);
+/* out = bf16(y_uncond + (y_cond - y_uncond) * scale): classifier-free guidance (generate.py:804) applied to the decoder
+ * outputs before the (linear, bias-free) vocabulary head, so that one head GEMM yields the guided logits. */
+int egom2p_cfg_combine_bf16(const float* y_uncond, const float* y_cond, int64_t n, float scale, uint16_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

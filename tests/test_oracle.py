@@ -105,3 +105,20 @@ def test_plan_egob_shapes(golden_dir):
     assert np.array_equal(dp["mask"], g["dec_mask"]) and np.array_equal(dp["mod_mask"], g["dec_mod"])
     assert np.array_equal(dp["target_ids"], g["target_ids"])
     assert np.array_equal(np.packbits(dp["attn_mask"], axis=-1), g["dec_attn"])
+
+
+def test_sampling_oracle_matches_reference_filter(golden_dir):
+    """oracle/sampling_oracle.py against what the unmodified reference's top_k_top_p_filtering / softmax keep and weigh
+    (tests/golden/sampling_filter.npz, generate.py:332-371)."""
+    import gen_golden_sampling as ggs
+    import sampling_oracle as so
+    g = np.load(os.path.join(golden_dir, "sampling_filter.npz"))
+    for name, rows, V, scale, top_k, top_p, temp in ggs.CASES:
+        lg = ggs.make_logits(name, rows, V, scale)
+        keep = so.kept_mask(lg, top_k, top_p)
+        want = np.unpackbits(g[name + "::keep"], axis=1)[:, :V].astype(bool)
+        # a token whose cumulative mass sits within float32 rounding of top_p may fall on either side
+        assert (keep != want).sum(1).max() <= 1, name
+        pr = so.probs(lg, temp, top_k, top_p)
+        assert np.array_equal(pr.argmax(1), g[name + "::argmax"]), name
+        np.testing.assert_allclose(pr.max(1), g[name + "::pmax"], rtol=2e-3)
