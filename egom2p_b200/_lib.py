@@ -46,7 +46,7 @@ SIGNATURES = {
     "egom2p_ce_dlogits": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, vp, i64, vp],
     "egom2p_attn_lse_stride": [i32],
     "egom2p_attn_ranges_bytes": [i32, i32],
-    "egom2p_attn_ranges": [vp, vp, i32, i32, i32, f32, vp, vp],
+    "egom2p_attn_ranges": [vp, vp, i32, i32, i32, f32, i32, vp, vp],
     "egom2p_attn_fwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp, vp, i64, vp, vp, vp],
     "egom2p_attn_bwd_scratch_bytes": [i32, i32, i32],
     "egom2p_attn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, f32, vp, vp, vp, vp,

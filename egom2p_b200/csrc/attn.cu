@@ -31,7 +31,8 @@ namespace egom2p {
 
 // ------------------------------------------------------------------------------------------------ range metadata
 __global__ void __launch_bounds__(256) attn_rows_kernel(const int32_t* __restrict__ key_lo, const int32_t* __restrict__ key_hi,
-                                                        int B, int Mq, int Nk, int S, float scale_log2, RangeMeta m) {
+                                                        int B, int Mq, int Nk, int S, float scale_log2, int empty_zero,
+                                                        RangeMeta m) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * S) return;
   const int b = (int)(i / S), r = (int)(i % S);
@@ -43,7 +44,10 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(const int32_t* __restric
     lo = max(lo, 0);
     hi = min(hi, Nk);
     rs = scale_log2;
-    if (hi <= lo) { lo = 0; hi = Nk; rs = 0.f; }  // every key masked -> uniform over all keys
+    if (hi <= lo) {
+      if (empty_zero) { lo = 0; hi = 0; }        // no key at all (the sampler's empty context): output exactly 0
+      else { lo = 0; hi = Nk; rs = 0.f; }        // every key masked -> uniform over all keys (masked_fill(-finfo.max), A4)
+    }
   }
   m.row_lo[i] = lo;
   m.row_hi[i] = hi;
@@ -491,7 +495,7 @@ extern "C" int egom2p_attn_lse_stride(int32_t Mq) { return egom2p::padS(Mq); }
 extern "C" int64_t egom2p_attn_ranges_bytes(int32_t B, int32_t Mq) { return egom2p::range_meta_bytes(B, Mq); }
 
 extern "C" int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, int32_t B, int32_t Mq, int32_t Nk, float scale,
-                                  void* meta, void* stream) {
+                                  int32_t empty_zero, void* meta, void* stream) {
   using namespace egom2p;
   EGO_REQUIRE(meta && B > 0 && Mq > 0 && Nk >= 0, "attn_ranges: bad argument");
   EGO_REQUIRE((key_lo == nullptr) == (key_hi == nullptr), "attn_ranges: key_lo / key_hi must both be given or both NULL");
@@ -499,7 +503,7 @@ extern "C" int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, 
   const int S = padS(Mq);
   RangeMeta m = carve_meta(meta, B, Mq);
   attn_rows_kernel<<<(unsigned)(((int64_t)B * S + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key_lo, key_hi, B, Mq, Nk, S,
-                                                                                           scale * kLog2e, m);
+                                                                                           scale * kLog2e, empty_zero, m);
   int rc = check_launch("attn_ranges rows");
   if (rc) return rc;
   attn_blocks_kernel<<<(B * (S / 64) + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, S, m);

@@ -723,6 +723,71 @@ class EgoM2P(nn.Module):
             out[mod] = self.decoder_embeddings[mod].forward_logits(rows)
         return out
 
+    # ------------------------------------------------------------------ generation path (egom2p_b200/generate.py)
+    @torch.no_grad()
+    def encode_tokens(self, mod_dict, masks: Dict[str, torch.Tensor], budget: int):
+        """Encoder half of one generation pass (reference: GenerationSampler.forward_mask_encoder_generation + forward_encoder
+        + decoder_proj_context, generate.py:407-444,749-757) straight from token ids: index plan over `masks` (the
+        modalities' input masks, possibly emptied for the unconditional branch), fused embed / gather of the `budget` kept
+        slots, the encoder blocks and the context projection. Returns (context (B, budget, D) fp32, n_valid (B,) int32);
+        no (B, L, D) embedding of the full modalities, no argsort, no host sync."""
+        enc_mods = [m for m in mod_dict if m in self.encoder_embeddings]
+        first = mod_dict[enc_mods[0]]["tensor"]
+        B, dev, D = first.shape[0], first.device, self.dim
+        ep = ops.index_plan([masks[m] for m in enc_mods], [self.modality_info[m]["id"] for m in enc_mods], budget)
+        N = ep.budget
+        lens, vocabs, ids, pos = self._tables("enc", enc_mods, mod_dict, B, dev)
+        x, emb = ops.embed_gather_fwd(ep, D, lens, vocabs, ids, [self.encoder_embeddings[m].token_emb.weight.detach() for m in enc_mods],
+                                      pos, [self.encoder_embeddings[m].mod_emb.detach().reshape(-1) for m in enc_mods])
+        x, emb = x.reshape(B * N, D), emb.reshape(B * N, D)
+        g = self._geom(B, N, 0)
+        g.enc_lo = torch.zeros(B, N, dtype=torch.int32, device=dev)
+        g.enc_hi = ep.n_valid[:, None].expand(B, N).contiguous()
+        g.build_meta(dev)
+        for i, blk in enumerate(self.encoder):
+            wqkv, wproj, w13, w2 = self._enc_weights(i)
+            x, _ = _self_attn_fwd(x, blk.norm1.weight.detach(), wqkv, wproj, B, N, g.H, g.m_enc, g.eps)
+            x, _ = _mlp_fwd(x, blk.norm2.weight.detach(), w13, w2, g.eps)
+        h, _, _, _ = ops.layernorm_fwd(x, self.encoder_norm.weight.detach(), self.eps, save_stats=False)
+        context = ops.linear_fwd(h, self._bf16("ctx", self.decoder_proj_context.weight), bias=self.decoder_proj_context.bias.detach(),
+                                 addend=emb, out_dtype=f32)
+        return context.reshape(B, N, D), ep.n_valid
+
+    @torch.no_grad()
+    def decode_tokens(self, y0: torch.Tensor, context: Optional[torch.Tensor], n_ctx: Optional[torch.Tensor]):
+        """Decoder half of one generation pass (generate.py:758-763 with decoder_attention_mask=None): y0 (B, k, D) fp32 decoder
+        inputs, context (B, N, D) fp32 with the first n_ctx[b] rows of sample b valid (a sample with n_ctx = 0 has NO context:
+        its cross-attention contributes exactly 0, SURVEY A5 (i) -- that is what lets the conditional and the unconditional
+        branch of guided decoding share one batch). Returns decoder_norm(y) as (B * k, D) fp32."""
+        B, M, D = y0.shape
+        dev = y0.device
+        N = 0 if context is None else context.shape[1]
+        g = self._geom(B, N, M)
+        if N > 0:
+            g.x_lo = torch.zeros(B, M, dtype=torch.int32, device=dev)
+            g.x_hi = n_ctx.to(torch.int32)[:, None].expand(B, M).contiguous()
+            g.m_x = ops.attn_ranges(B, M, N, g.x_lo, g.x_hi, device=dev, empty_zero=True)
+            c = context.reshape(B * N, D)
+        g.m_dec = ops.attn_ranges(B, M, M, device=dev)
+        h = y0.reshape(B * M, D).float().contiguous()
+        for i, blk in enumerate(self.decoder):
+            wqkv, wsproj, wq, wkv, wxproj, w13, w2 = self._dec_weights(i)
+            h, _ = _self_attn_fwd(h, blk.norm1.weight.detach(), wqkv, wsproj, B, M, g.H, g.m_dec, g.eps)
+            if N > 0:
+                hq, _, _, _ = ops.layernorm_fwd(h, blk.query_norm.weight.detach(), g.eps, save_stats=False)
+                q = ops.linear_fwd(hq, wq)
+                hc, _, _, _ = ops.layernorm_fwd(c, blk.context_norm.weight.detach(), g.eps, save_stats=False)
+                kv = ops.linear_fwd(hc, wkv)
+                o2, _ = ops.attn_fwd(q, kv[:, :D], kv[:, D:], B, g.H, M, N, meta=g.m_x, want_lse=False)
+                h = ops.linear_fwd(o2, wxproj, addend=h, out_dtype=f32)
+            h, _ = _mlp_fwd(h, blk.norm2.weight.detach(), w13, w2, g.eps)
+        _, yn, _, _ = ops.layernorm_fwd(h, self.decoder_norm.weight.detach(), self.eps, out_bf16=False, out_f32=True, save_stats=False)
+        return yn
+
+    def head_operand(self, mod: str) -> torch.Tensor:
+        """Cached bf16 operand of a modality's vocabulary head (V, D)."""
+        return self._bf16(("head", mod), self.decoder_embeddings[mod].to_logits.weight)
+
     def _geom(self, B, N, M) -> _Geom:
         g = _Geom()
         g.B, g.N, g.M, g.H, g.D, g.eps = B, N, M, self.num_heads, self.dim, self.eps

@@ -320,13 +320,14 @@ def lse_stride(Mq: int) -> int:
     return int(_lib.load().egom2p_attn_lse_stride(Mq))
 
 
-def attn_ranges(B, Mq, Nk, key_lo=None, key_hi=None, scale=None, device=None):
-    """Range metadata of one (plan, attention kind), built once per forward and shared by all layers / heads."""
+def attn_ranges(B, Mq, Nk, key_lo=None, key_hi=None, scale=None, device=None, empty_zero=False):
+    """Range metadata of one (plan, attention kind), built once per forward and shared by all layers / heads.
+    empty_zero: rows with an empty range get output 0 instead of uniform attention (inference only)."""
     lib = _lib.load()
     scale = (64 ** -0.5) if scale is None else scale
     device = device if device is not None else key_lo.device
     meta = torch.empty(lib.egom2p_attn_ranges_bytes(B, Mq), dtype=torch.uint8, device=device)
-    _lib.check(lib.egom2p_attn_ranges(_p(key_lo), _p(key_hi), B, Mq, Nk, scale, _p(meta), _s()), "attn_ranges")
+    _lib.check(lib.egom2p_attn_ranges(_p(key_lo), _p(key_hi), B, Mq, Nk, scale, int(empty_zero), _p(meta), _s()), "attn_ranges")
     return meta
 
 

@@ -149,9 +149,13 @@ int egom2p_ce_dlogits(const uint16_t* Y, const uint16_t* W, const int64_t* targe
 int egom2p_attn_lse_stride(int32_t Mq);                 /* S = Mq rounded up to 128 */
 int64_t egom2p_attn_ranges_bytes(int32_t B, int32_t Mq); /* bytes of the range metadata buffer */
 /* Builds the per-row / per-block range metadata once per forward; it is shared by every layer and head and by the
- * forward and backward kernels. key_lo / key_hi are (B, Mq) int32 or both NULL. meta: 256-byte aligned. */
+ * forward and backward kernels. key_lo / key_hi are (B, Mq) int32 or both NULL. meta: 256-byte aligned.
+ * empty_zero = 0: a row with an empty range attends all Nk keys uniformly (the reference's masked_fill(-finfo.max));
+ * empty_zero = 1: such a row has NO keys and its output is exactly 0 -- a sample whose context is empty inside a batch
+ * that also holds non-empty contexts (the unconditional branch of guided decoding, egom2p/models/generate.py:793-802,
+ * batched with the conditional one). Forward only. */
 int egom2p_attn_ranges(const int32_t* key_lo, const int32_t* key_hi, int32_t B, int32_t Mq, int32_t Nk, float scale,
-                       void* meta, void* stream);
+                       int32_t empty_zero, void* meta, void* stream);
 /* lse is (B, H, S) fp32 in log2 units (reference + log2(sum) of scale*log2e*scores), saved for the backward pass.
  * kmax_scratch: B*H floats of device scratch for the pre-pass of the bound-path softmax (max_k |k|^2 per batch and head,
  * see csrc/attn.cu), or NULL to force the online-maximum softmax. */
