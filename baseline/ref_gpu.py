@@ -98,6 +98,63 @@ def time_reference(batch: int, steps: int, warmup: int, device: torch.device, ma
     return out
 
 
+GEN_WORKLOADS = {  # eval_model_rgb2depth.py:45-59, eval_model_rgb2cam.py:40-54, eval_model_rgb2gaze.py:41-55, eval_model_depth2rgb.py:34-48
+    "rgb2depth": dict(cond="tok_rgb", target="tok_depth", ntoks=5120, steps=3),
+    "rgb2cam": dict(cond="tok_rgb", target="tok_cam", ntoks=30, steps=3),
+    "rgb2gaze": dict(cond="tok_rgb", target="tok_gaze", ntoks=30, steps=5),
+    "depth2rgb": dict(cond="tok_depth", target="tok_rgb", ntoks=5120, steps=6),
+}
+
+
+def time_reference_generation(workload: str, batch: int, reps: int, warmup: int, device: torch.device) -> dict:
+    """Latency of the reference's own generation (GenerationSampler.generate, guided ROAR, T = 0.01, top-p 0.8, CFG 2.0) for one
+    batch of `batch` clips, exactly as the eval scripts set it up: fp32 with TF32 matmuls allowed, no autocast, no grad."""
+    MI, create_model = import_reference()
+    from egom2p.models.generate import (GenerationSampler, build_chained_generation_schedules, init_empty_target_modality,
+                                        init_full_input_modality)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    w = GEN_WORKLOADS[workload]
+    torch.manual_seed(0)
+    model = create_model("egom2p_base_12e_12d_swiglu_nobias",
+                         encoder_embeddings={m: MI[m]["encoder_embedding"]() for m in MODS},
+                         decoder_embeddings={m: MI[m]["decoder_embedding"]() for m in MODS},
+                         modality_info={m: MI[m] for m in MODS}, num_register_tokens=0).eval().to(device)
+    sampler = GenerationSampler(model)
+    schedule = build_chained_generation_schedules(
+        cond_domains=[w["cond"]], target_domains=[w["target"]], tokens_per_target=[w["ntoks"]], autoregression_schemes=["roar"],
+        decoding_steps=[w["steps"]], token_decoding_schedules=["linear"], temps=[0.01], temp_schedules=["constant"],
+        cfg_scales=[2.0], cfg_schedules=["constant"], cfg_grow_conditioning=True)
+    g = torch.Generator().manual_seed(1)
+
+    def one():
+        md = {w["cond"]: {"tensor": torch.randint(0, 64000, (batch, 5, 32, 32), generator=g).to(device),
+                          "input_mask": torch.zeros(batch, 5120, dtype=torch.bool, device=device),
+                          "target_mask": torch.ones(batch, 5120, dtype=torch.bool, device=device)}}
+        md = init_empty_target_modality(md, MI, w["target"], batch, w["ntoks"], device)
+        md = init_full_input_modality(md, MI, w["cond"], device)
+        out = sampler.generate(md, schedule, verbose=False, seed=0, top_p=0.8, top_k=0.0)
+        return out[w["target"]]["tensor"].sum().item()
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            one()
+        e1.record()
+        torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    out = {"workload": workload, "batch": batch, "ms_per_call": ms, "clips_per_s": batch / (ms / 1e3), "reps": reps,
+           "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
+           "what": "unmodified reference GenerationSampler.generate (baseline/_ref), fp32 + TF32, same GPU"}
+    del model, sampler
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, nargs="+", default=[4])

@@ -254,6 +254,115 @@ def cpu_reference_step(b: int, threads: int):
     return time.perf_counter() - t0, float(out["loss"])
 
 
+GEN_WORKLOADS = {  # eval_model_rgb2depth.py:45-59, eval_model_rgb2cam.py:40-54, eval_model_rgb2gaze.py:41-55, eval_model_depth2rgb.py:34-48
+    "rgb2depth": dict(cond="tok_rgb", target="tok_depth", ntoks=5120, steps=3, batch=1, config=2),
+    "rgb2cam": dict(cond="tok_rgb", target="tok_cam", ntoks=30, steps=3, batch=1, config=3),
+    "rgb2gaze": dict(cond="tok_rgb", target="tok_gaze", ntoks=30, steps=5, batch=1, config=3),
+    "depth2rgb": dict(cond="tok_depth", target="tok_rgb", ntoks=5120, steps=6, batch=64, config=4),
+}
+
+
+def generation_flops(w, schedule) -> float:
+    """Algorithmic FLOPs of one clip through guided ROAR decoding in this repo's formulation (SURVEY.md section 8(d) formulas):
+    per step a conditional and an unconditional encoder pass at their own lengths, one decoder pass per branch, ONE head."""
+    D, F, Le, Ld = 768, 2048, 12, 12
+    V = SHAPES[w["target"]][1]
+    enc = lambda n: 2.0 * (Le * (n * (4 * D * D + 3 * D * F) + 2 * n * n * D) + n * D * D)
+    dec = lambda k, n: 2.0 * Ld * (k * (6 * D * D + 3 * D * F) + 2 * n * D * D + 2 * k * k * D + 2 * k * n * D)
+    done, total = 0, 0.0
+    for st in schedule:
+        k = int(st["num_tokens"])
+        n_c, n_u = SHAPES[w["cond"]][0] + done, done
+        total += enc(n_c) + enc(n_u) + dec(k, n_c) + dec(k, n_u) + 2.0 * k * D * V
+        done += k
+    return total
+
+
+def run_generation(args):
+    """BASELINE.json configs[2..4]: latency / throughput of guided ROAR generation through egom2p_b200.generate.GenerationSampler
+    on synthetic conditioning tokens and random-init ego-b weights, with the unmodified reference sampler timed on the same GPU."""
+    from egom2p_b200 import _lib
+    from egom2p_b200.generate import GenerationSampler, build_chained_generation_schedules, init_empty_target_modality, init_full_input_modality
+    w = GEN_WORKLOADS[args.workload]
+    B = args.batch if args.batch_given else w["batch"]
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    model = build_model(dev).eval()
+    info = model.modality_info
+    sampler = GenerationSampler(model)
+    schedule = build_chained_generation_schedules(
+        cond_domains=[w["cond"]], target_domains=[w["target"]], tokens_per_target=[w["ntoks"]], autoregression_schemes=["roar"],
+        decoding_steps=[w["steps"]], token_decoding_schedules=["linear"], temps=[0.01], temp_schedules=["constant"],
+        cfg_scales=[2.0], cfg_schedules=["constant"], cfg_grow_conditioning=True)
+    rng = np.random.default_rng(1234)
+    n_calls = args.warmup + args.steps + 1
+    host = [torch.from_numpy(rng.integers(0, 64000, size=(B, 5, 32, 32), dtype=np.int64)).pin_memory() for _ in range(n_calls)]
+    devt = [t.to(dev) for t in host]
+
+    def call(tokens):
+        md = {w["cond"]: {"tensor": tokens}}
+        md = init_empty_target_modality(md, info, w["target"], B, w["ntoks"], dev)
+        md = init_full_input_modality(md, info, w["cond"], dev)
+        return sampler.generate(md, schedule, top_p=0.8, top_k=0.0, seed=0)[w["target"]]["tensor"]
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            call(devt[i])
+        sampler_clk = ClockSampler(0)
+        sampler_clk.start()
+        l0 = _lib.launch_count()
+        ms = timed(lambda i: call(devt[args.warmup + i]), args.steps)
+        launches = _lib.launch_count() - l0
+        clocks = sampler_clk.stop()
+        ms_e2e = timed(lambda i: call(host[args.warmup + i].to(dev, non_blocking=True)).cpu(), args.steps)
+    t_call = ms / args.steps / 1e3
+    flops = generation_flops(w, schedule) * B
+    hbm, tf_burst, tf_sus, src = peaks()
+    tfl = flops / t_call / 1e12
+    line = {"metric": f"{args.workload} guided ROAR generation clips/sec", "value": B / t_call, "unit": "clips/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_call * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[{w['config']}]: {args.workload}, ego-b (396.2M) random-init, {SHAPES[w['cond']][0]} conditioning tokens -> "
+                                   f"{w['ntoks']} target tokens in {w['steps']} ROAR steps, T = 0.01, top-p 0.8, CFG 2.0 (cond + uncond branch per step), "
+                                   f"batch {B} clips per call; one step = one generate() call",
+                       "batch": B, "latency_ms_per_clip_batch": t_call * 1e3, "algorithmic_tflop_per_call": flops / 1e12,
+                       "model_tflops": tfl, "mfu_vs_2250_spec": tfl / 2250.0, "mfu_vs_measured_sustained": tfl / tf_sus,
+                       "l2_policy": "fresh conditioning tokens every call; activations exceed L2 for the video targets"},
+            "e2e": {"value": B / (ms_e2e / args.steps / 1e3), "unit": "clips/s", "h2d_bytes_per_step": int(host[0].numel() * 8),
+                    "d2h_bytes_per_step": int(B * w["ntoks"] * 8)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "whole generate() call (GEMM + attention kernels)", "achieved": tfl, "peak": tf_sus,
+                         "unit": "TFLOP/s", "frac": tfl / tf_sus, "traffic": None, "peak_source": f"{src} bf16_tflops_sustained"}}
+    if not args.no_reference_gpu:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import ref_gpu
+        if ref_gpu.available():
+            del sampler, model
+            torch.cuda.empty_cache()
+            res = []
+            for rb in sorted({1, min(B, 4)}):
+                try:
+                    res.append(ref_gpu.time_reference_generation(args.workload, rb, 2, 1, dev))
+                except torch.cuda.OutOfMemoryError:
+                    res.append({"workload": args.workload, "batch": rb, "oom": True})
+                    torch.cuda.empty_cache()
+            line["reference_gpu"] = res
+            best = max((r["clips_per_s"] for r in res if "clips_per_s" in r), default=None)
+            if best:
+                line["reference_gpu_speedup"] = line["value"] / best
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -283,7 +392,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("EGOM2P_BENCH_BATCH", "32")), help="samples per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (training: default 32; generation: the workload's batch)")
+    ap.add_argument("--workload", default="train", choices=["train"] + list(GEN_WORKLOADS),
+                    help="train: the ego-b mod4 training step (the headline, BASELINE configs[1]); others: guided ROAR generation (configs[2..4])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--regime", default="dense", choices=["dense", "reference-masks"],
                     help="dense: SURVEY 8(d) headline synthetic regime; reference-masks: ragged masks drawn by the reference's UnifiedMasking")
@@ -296,6 +407,15 @@ def main():
                     help="skip timing the unmodified reference (baseline/_ref, eager bf16 autocast) on this GPU (N = 1 only)")
     ap.add_argument("--cpu-steps", type=int, default=1)
     args = ap.parse_args()
+    args.batch_given = args.batch is not None
+    if args.batch is None:
+        args.batch = int(os.environ.get("EGOM2P_BENCH_BATCH", "32"))
+    if args.workload != "train":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm times the training step only (--workload train)"}))
+            return
+        args.warmup = max(args.warmup, 1) if args.workload == "depth2rgb" else max(args.warmup, 3)
+        return run_generation(args)
     if args.impl == "reference":
         args.steps = min(args.steps, 2)
         args.warmup = min(args.warmup, 1)
