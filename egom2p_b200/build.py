@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libegom2p_b200.so")
-SOURCES = ["capi.cu", "plan.cu", "embed.cu", "norm.cu", "elementwise.cu", "gemm.cu", "attn.cu", "attn_bwd.cu", "sample.cu"]
+SOURCES = ["capi.cu", "plan.cu", "embed.cu", "norm.cu", "elementwise.cu", "gemm.cu", "attn.cu", "attn_bwd.cu", "sample.cu", "masking.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

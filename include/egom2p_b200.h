@@ -218,6 +218,18 @@ int egom2p_gather_rows_bf16(const uint16_t* src, const int64_t* idx, int64_t n, 
 int egom2p_scatter_rows_f32(const float* src, const int64_t* idx, int64_t n, int32_t cols, float* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side masking of the token modalities: UnifiedMasking.image_mask (egom2p/data/masking.py:236-266) for a whole batch
+ * of one modality. Positions are ranked by a random key per position (32-bit Philox draws from (seed, offset), subsequences
+ * separated by stream_id; or the caller's noise (B, L) fp32 >= 0, ordered like a stable argsort): with ids_shuffle =
+ * argsort(keys), position r is an input (input_mask 0) iff ids_shuffle[r] < input_budget[b] and a target (target_mask 0) iff
+ * input_budget[b] <= ids_shuffle[r] < input_budget[b] + target_budget[b] (NULL: all the rest) -- the reference's gather --
+ * and attn_cnt holds the target count at the lowest target position (0 elsewhere). L <= 8192.
+ * ------------------------------------------------------------------------------------------------ */
+int egom2p_image_masks(const float* noise, uint64_t seed, uint64_t offset, int32_t stream_id, int32_t B, int32_t L,
+                       const int32_t* input_budget, const int32_t* target_budget, uint8_t* input_mask, uint8_t* target_mask,
+                       int32_t* attn_cnt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Generation (guided ROAR / MaskGIT decoding, egom2p/models/generate.py): fused sampling.
  * ------------------------------------------------------------------------------------------------ */
 /* One token per row from fp32 logits (rows, V), row pitch ld, with the semantics of GenerationSampler.sample_tokens /
