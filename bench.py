@@ -400,6 +400,8 @@ def main():
                     help="dense: SURVEY 8(d) headline synthetic regime; reference-masks: ragged masks drawn by the reference's UnifiedMasking")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: egom2p_b200.optim.FusedAdamW (multi-tensor clip + AdamW); torch: clip_grad_norm_ + torch.optim.AdamW(fused=True)")
+    ap.add_argument("--allreduce", default="fp32", choices=["fp32", "bf16"],
+                    help="gradient all-reduce precision for N > 1 (fp32 = the reference's DDP default; bf16 = torch's bf16_compress_hook)")
     ap.add_argument("--no-batch4", action="store_true", help="skip the extra b = 4 per GPU measurement (the reference's own batch size; N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the b = 1 full-size parity gate against the reference's fp32 outputs")
@@ -441,6 +443,9 @@ def main():
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
                                                         broadcast_buffers=False, gradient_as_bucket_view=True)
+        if args.allreduce == "bf16":   # optional gradient compression: halves the NVLink bytes of the overlapped all-reduce
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     decay = [p for n, p in model.named_parameters() if not ("norm" in n or n.endswith(".bias"))]
     no_decay = [p for n, p in model.named_parameters() if ("norm" in n or n.endswith(".bias"))]
     groups = [{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}]
@@ -541,6 +546,17 @@ def main():
                   "eager": dict(mk4(ms4), launches_per_step=l4),
                   "cuda_graph": dict(mk4(ms4g), launches_per_step=1, note="whole step (fwd + bwd + clip + AdamW) replayed as one graph")}
 
+    # ---- data-parallel consistency: after the timed steps every rank must hold the same weights (same all-reduced gradients,
+    # same optimizer arithmetic); checked on a checksum of all parameters
+    ddp_check = None
+    if world > 1:
+        chk = torch.stack([torch.stack([p.detach().double().sum(), p.detach().double().abs().sum()]) for p in model.parameters()]).sum(0)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        allc = torch.stack(allc)
+        ddp_check = {"ranks": world, "weights_identical_across_ranks": bool((allc == allc[0]).all()),
+                     "checksum": [float(v) for v in allc[0]], "allreduce": args.allreduce}
+
     # ---- per-kernel-family breakdown of one extra step (CUDA events around each C-ABI launch)
     with ops.KernelTimer() as kt:
         step(dev_batches[0])
@@ -575,6 +591,7 @@ def main():
             "gpu_launches": int(launches),
             "parity": parity,
             "batch4": batch4,
+            "ddp": ddp_check,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all nn.Linear fwd/dgrad/wgrad)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,

@@ -135,7 +135,10 @@ __device__ __forceinline__ OptItem find_item(const OptItem* __restrict__ items, 
   return *sh;
 }
 
-__global__ void __launch_bounds__(kEwThreads) sumsq_multi_kernel(const OptItem* __restrict__ items, int n_items, float* __restrict__ out) {
+// Deterministic: one partial sum per block, then a single block adds the partials in a fixed order. Under data parallelism
+// every rank must compute the SAME clip coefficient from the same all-reduced gradients, or the replicas' weights drift apart
+// in the last bits (nothing re-synchronises weights in DDP) -- so no floating-point atomics here.
+__global__ void __launch_bounds__(kEwThreads) sumsq_multi_kernel(const OptItem* __restrict__ items, int n_items, float* __restrict__ partials) {
   __shared__ OptItem sh_it;
   const OptItem it = find_item(items, n_items, &sh_it);
   const int64_t e0 = ((int64_t)blockIdx.x - it.first_chunk) * kOptChunk;
@@ -159,8 +162,20 @@ __global__ void __launch_bounds__(kEwThreads) sumsq_multi_kernel(const OptItem* 
   if (threadIdx.x < 32) {
     float t = threadIdx.x < kEwThreads / 32 ? sh[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
   }
+}
+__global__ void __launch_bounds__(1024) sumsq_finalize_kernel(const float* __restrict__ partials, int64_t n, float* __restrict__ out) {
+  double acc = 0.0;   // thread t adds partials t, t + 1024, ... in order; the 1024 sums are then added in a fixed tree
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (double)partials[i];
+  __shared__ double sh[1024];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)sh[0];
 }
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float lr, float wd, float b1, float b2, float eps,
@@ -286,13 +301,15 @@ extern "C" int egom2p_add_f32(const float* a, const float* b, int64_t n, float* 
   add_kernel<<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)stream>>>(a, b, n, out, out_bf16);
   return check_launch("add_f32");
 }
-extern "C" int egom2p_sumsq_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float* sumsq, void* stream) {
+extern "C" int egom2p_sumsq_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float* partials, float* sumsq,
+                                  void* stream) {
   using namespace egom2p;
-  EGO_REQUIRE(items_dev && sumsq && n_items > 0 && n_chunks > 0 && n_chunks < (int64_t)INT32_MAX, "sumsq_multi: bad argument");
-  cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(float), (cudaStream_t)stream);
-  if (e != cudaSuccess) { set_error("sumsq_multi: memset: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
-  sumsq_multi_kernel<<<(unsigned)n_chunks, kEwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const OptItem*>(items_dev), n_items, sumsq);
-  return check_launch("sumsq_multi");
+  EGO_REQUIRE(items_dev && sumsq && partials && n_items > 0 && n_chunks > 0 && n_chunks < (int64_t)INT32_MAX, "sumsq_multi: bad argument");
+  sumsq_multi_kernel<<<(unsigned)n_chunks, kEwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const OptItem*>(items_dev), n_items, partials);
+  int rc = check_launch("sumsq_multi");
+  if (rc) return rc;
+  sumsq_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_chunks, sumsq);
+  return check_launch("sumsq_multi finalize");
 }
 extern "C" int egom2p_adamw_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float beta1, float beta2, float eps,
                                   int32_t* step_dev, const float* sumsq, float max_norm, void* stream) {

@@ -47,6 +47,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step_dev: Optional[torch.Tensor] = None
         self._sumsq: Optional[torch.Tensor] = None
         self._pending_clip: Optional[float] = None
+        self._partials: Optional[torch.Tensor] = None
         self.bytes_per_step = 0.0
 
     # ------------------------------------------------------------------ device table
@@ -90,6 +91,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._stage.copy_(raw)
         self._table.copy_(self._stage, non_blocking=True)
         self._sig, self._n_items, self._n_chunks = sig, len(live), chunk
+        if self._partials is None or self._partials.numel() < chunk:
+            self._partials = torch.empty(chunk, dtype=torch.float32, device=dev)
         self.bytes_per_step = nbytes * 28.0
         self._grad_bytes = nbytes * 4.0
         return True
@@ -104,7 +107,8 @@ class FusedAdamW(torch.optim.Optimizer):
             return torch.zeros(())
         lib = _lib.load()
         with _timed("optimizer", self._grad_bytes, "byte"):
-            _lib.check(lib.egom2p_sumsq_multi(_p(self._table), self._n_items, self._n_chunks, _p(self._sumsq), _s()), "sumsq_multi")
+            _lib.check(lib.egom2p_sumsq_multi(_p(self._table), self._n_items, self._n_chunks, _p(self._partials), _p(self._sumsq), _s()),
+                       "sumsq_multi")
         self._pending_clip = float(max_norm)
         return self._sumsq.sqrt().reshape(())
 

@@ -194,7 +194,8 @@ int egom2p_add_f32(const float* a, const float* b, int64_t n, float* out, uint16
  * NativeScalerWithGradNormCount.__call__, egom2p/utils/native_scaler.py:27-47; AdamW groups from
  * egom2p/utils/optim_factory.py:206-226). The item table lives in device memory; first_chunk = running sum of
  * ceil(n / 8192) over the items before i, n_chunks = the total.
- *   egom2p_sumsq_multi: *sumsq = sum over all items of sum(g^2) (zeroed inside, fp32 atomics).
+ *   egom2p_sumsq_multi: *sumsq = sum over all items of sum(g^2); deterministic (per-chunk partial sums in `partials`,
+ *     n_chunks floats of scratch, added in a fixed order) so that data-parallel replicas compute identical clip factors.
  *   egom2p_adamw_multi: torch.optim.AdamW update of every item with its own lr / weight decay; the gradient is read as
  *     g * min(1, max_norm / (sqrt(*sumsq) + 1e-6)) when sumsq != NULL (clip folded in: gradients are not rewritten);
  *     bias corrections use *step_dev + 1, and *step_dev is incremented afterwards (CUDA-graph capturable). */
@@ -207,7 +208,7 @@ typedef struct {
   int64_t first_chunk;
   float lr, weight_decay;
 } egom2p_opt_item;
-int egom2p_sumsq_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float* sumsq, void* stream);
+int egom2p_sumsq_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float* partials, float* sumsq, void* stream);
 int egom2p_adamw_multi(const void* items_dev, int32_t n_items, int64_t n_chunks, float beta1, float beta2, float eps,
                        int32_t* step_dev, const float* sumsq, float max_norm, void* stream);
 /* out[c] += sum_r x[r, c] -- bias gradient of decoder_proj_context (egom2p_model.py:157,722). */
