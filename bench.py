@@ -108,9 +108,11 @@ def step_flops(md) -> float:
         for m in mods:
             kept[m] = min(n_tg[m], left)
             left -= kept[m]
-        enc = Le * (N * (4 * D * D + 3 * D * F) + 2 * N * n_enc * D)
-        ctx = N * D * D
-        dec = Ld * (M * (6 * D * D + 3 * D * F) + 2 * N * D * D + 2 * sum(v * v for v in kept.values()) * D + 2 * M * n_enc * D)
+        n_dec = sum(kept.values())
+        # valid tokens only: pad slots are don't-care rows that the packed layout does not even compute
+        enc = Le * (n_enc * (4 * D * D + 3 * D * F) + 2 * n_enc * n_enc * D)
+        ctx = n_enc * D * D
+        dec = Ld * (n_dec * (6 * D * D + 3 * D * F) + 2 * n_enc * D * D + 2 * sum(v * v for v in kept.values()) * D + 2 * n_dec * n_enc * D)
         head = sum(kept[m] * D * MI[m]["vocab_size"] for m in mods)
         total += 3 * 2.0 * (enc + ctx + dec + head)
     return total

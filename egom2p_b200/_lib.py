@@ -34,8 +34,8 @@ SIGNATURES = {
     "egom2p_launch_count": [],
     "egom2p_index_plan": [C.POINTER(PlanDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "egom2p_plan_rows": [vp, i64, C.POINTER(i32), i32, i64, vp, vp, vp],
-    "egom2p_embed_gather_fwd": [C.POINTER(EmbedDesc), vp, vp, vp, vp, i64, i32, vp, vp, vp],
-    "egom2p_embed_gather_bwd": [C.POINTER(EmbedDesc), vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp],
+    "egom2p_embed_gather_fwd": [C.POINTER(EmbedDesc), vp, vp, vp, vp, vp, i64, i32, vp, vp, vp],
+    "egom2p_embed_gather_bwd": [C.POINTER(EmbedDesc), vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp],
     "egom2p_layernorm_fwd": [vp, vp, i64, i32, f32, vp, vp, vp, vp, vp],
     "egom2p_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp],
     "egom2p_gemm_bf16": [vp, vp, i32, i32, i32, i64, i64, i32, i32, vp, vp, i64, vp, vp, i64, vp],

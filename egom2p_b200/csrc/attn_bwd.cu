@@ -4,7 +4,8 @@
 // it. Keys sit on the TMEM lanes. Per block, five tcgen05 MMAs (all M = 128):
 //     S^T  = K Q^T         (TMEM fp32)        dP^T = V dO^T       (TMEM fp32)
 //     P^T  = exp2(S^T*c - lse_q), dS^T = P^T * (dP^T*scale - delta_q*scale)       (math warps)
-//     dV  += P^T dO        A = P^T  read from TMEM (bf16, written with tcgen05.st)
+//     (K and V sit in TMEM as packed bf16 -- copied once per CTA -- and are the TMEM A operands of the first two products)
+//     dV  += P^T dO        A = P^T  read from TMEM (bf16, written with tcgen05.st in place over the thread's own S^T columns)
 //     dK  += dS^T Q        A = dS^T read from TMEM (written in place over the dP^T columns)
 //     dQ   = dS K          A = dS^T read MN-major from swizzled smem -> TMEM -> fp32 accumulator in HBM (TMA reduce-add)
 // so S and dP are produced once per (key tile, query block) pair (10 tile-GEMM units instead of 14 for separate
@@ -74,6 +75,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float4 lds_f4(const void* p) {  // 16-byte shared load (a warp-wide broadcast when p is uniform)
   float4 v;
@@ -106,7 +115,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* dq_full = ds_empty + 1;            // dQ block in TMEM
   uint64_t* dq_free = dq_full + 1;             // drain warps hold dQ in registers
   uint64_t* dkv_full = dq_free + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
+  uint64_t* kv_tmem = dkv_full + 1;             // K / V copied to TMEM by the math warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_tmem + 1);
   int* s_n = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,6 +131,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(ds_full, kBwdMathWarps); mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);  mbar_init(dq_free, 4);
     mbar_init(dkv_full, 1);
+    mbar_init(kv_tmem, kBwdMathWarps);
     fence_mbar_init();
     // the K / V tile does not depend on the query-block list: its load overlaps the list build and the TMEM allocation
     mbar_expect_tx(kv_full, 2 * BwdSmem::kTile);
@@ -185,7 +196,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n = *s_n;
-  constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 320, cDQ = 384, cPT = 448;  // TMEM columns (cPT: P^T as bf16 pairs)
+  // TMEM columns. P^T (bf16 pairs) is written in place over the first 32 of each thread's 64 S^T columns (k-steps 0-3 at
+  // columns 0-31, 4-7 at columns 64-95, like dS^T over dP^T), which frees 64 columns for K and V as packed bf16: the S^T and
+  // dP^T products read their A operand from TMEM instead of shared memory (-32 KB of the 272 KB of shared-memory traffic per
+  // 128 x 128 block that bound this kernel).
+  constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 320, cDQ = 384, cK = 448, cV = 480;
 
   if (warp >= kBwdTmaWarp) {
     if (warp == kBwdTmaWarp) {
@@ -205,17 +220,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kT, 0, 0);    // S^T, dP^T: K-major x K-major, N = 128
         constexpr uint32_t idesc_tm = umma_idesc_bf16(128, kD, 0, 1);    // dV, dK: A in TMEM x MN-major B, N = 64
         constexpr uint32_t idesc_mm = umma_idesc_bf16(128, kD, 1, 1);    // dQ: MN-major x MN-major, N = 64
-        const uint32_t tS = tmem_base + cS, tDP = tmem_base + cDP, tDV = tmem_base + cDV, tDK = tmem_base + cDK,
-                       tDQ = tmem_base + cDQ, tPT = tmem_base + cPT;
-        const uint64_t dK0 = umma_desc_kmajor_sw128(smem_u32(sK)), dV0 = umma_desc_kmajor_sw128(smem_u32(sV));
+        const uint32_t tS = tmem_base + cS, tDP = tmem_base + cDP, tDQ = tmem_base + cDQ, tK = tmem_base + cK, tV = tmem_base + cV;
         const uint64_t dKm0 = umma_desc_mnmajor_sw128(smem_u32(sK), 8192);
         const uint64_t dDSm0 = umma_desc_mnmajor_sw128(smem_u32(sDS), BwdSmem::kTile);
         auto issue_s = [&](int st) {
           const uint64_t dQ0 = umma_desc_kmajor_sw128(smem_u32(sQ + st * BwdSmem::kTile));
           if (elect_one()) {
-            umma_bf16_ss(tS, dK0, dQ0, idesc_kk, 0u);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_bf16_ss(tS, dK0 + 2 * k, dQ0 + 2 * k, idesc_kk, 1u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(tS, tK + 8 * k, dQ0 + 2 * k, idesc_kk, k ? 1u : 0u);
             umma_commit(s_full);
           }
           __syncwarp();
@@ -223,9 +235,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto issue_dp = [&](int st) {
           const uint64_t dDO0 = umma_desc_kmajor_sw128(smem_u32(sDO + st * BwdSmem::kTile));
           if (elect_one()) {
-            umma_bf16_ss(tDP, dV0, dDO0, idesc_kk, 0u);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_bf16_ss(tDP, dV0 + 2 * k, dDO0 + 2 * k, idesc_kk, 1u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(tDP, tV + 8 * k, dDO0 + 2 * k, idesc_kk, k ? 1u : 0u);
             umma_commit(dp_full);
           }
           __syncwarp();
@@ -233,7 +244,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // One issuing thread sustains one tcgen05.mma per ~60 cycles whatever N <= 128 is (tools/micro/bench_umma.cu), so the
         // 32 MMAs of a block are split over two issuer warps: this one S^T, dP^T and dQ, warp B dV and dK. MMAs of
         // different issuers are not ordered against each other: every cross dependency goes through an mbarrier.
-        mbar_wait(kv_full, 0);
+        mbar_wait(kv_tmem, 0);
         mbar_wait(&q_full[0], 0);
         tc_fence_after();
         issue_s(0);
@@ -241,9 +252,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int idx = 0; idx < n; ++idx) {
           const int st1 = (idx + 1) % kBwdStages;
           const uint32_t par = idx & 1;
-          if (idx + 1 < n) {  // S^T of the next block as soon as this block's scores sit in registers
+          if (idx + 1 < n) {  // S^T of the next block once this block's scores sit in registers AND its P^T (written over
+                              // them) has been consumed by the dV product; the math warps are busy with dS^T meanwhile
             mbar_wait(&q_full[st1], ((idx + 1) / kBwdStages) & 1);
             mbar_wait(s_free, par);
+            mbar_wait(p_empty, par);
             tc_fence_after();
             TRACE(0, idx);
             issue_s(st1);
@@ -272,7 +285,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ------------------------------------------------------------------------------------------ MMA issuer B: dV, dK
       if (n > 0) {
         constexpr uint32_t idesc_tm = umma_idesc_bf16(128, kD, 0, 1);    // A in TMEM x MN-major B, N = 64
-        const uint32_t tDP = tmem_base + cDP, tDV = tmem_base + cDV, tDK = tmem_base + cDK, tPT = tmem_base + cPT;
+        const uint32_t tS = tmem_base + cS, tDP = tmem_base + cDP, tDV = tmem_base + cDV, tDK = tmem_base + cDK;
         for (int idx = 0; idx < n; ++idx) {
           const int st = idx % kBwdStages;
           const uint32_t par = idx & 1;
@@ -283,7 +296,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint64_t dDOm0 = umma_desc_mnmajor_sw128(smem_u32(sDO + st * BwdSmem::kTile), 8192);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) umma_bf16_ts(tDV, tPT + 8 * k, dDOm0 + 128 * k, idesc_tm, (idx | k) ? 1u : 0u);
+            for (int k = 0; k < 8; ++k)
+              umma_bf16_ts(tDV, tS + (k < 4 ? 8 * k : 64 + 8 * (k - 4)), dDOm0 + 128 * k, idesc_tm, (idx | k) ? 1u : 0u);
             umma_commit(p_empty);
           }
           __syncwarp();
@@ -352,6 +366,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint8_t* pDS = sDS + half * BwdSmem::kTile;
     const float SC = p.scale_log2, RN = p.scale_log2 * kLn2;
+    if (n > 0) {   // K, V: smem -> TMEM (this thread's key row, its half of the head dim = 16 packed columns each)
+      mbar_wait(kv_full, 0);
+      uint32_t kw[16], vw[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = *reinterpret_cast<const uint4*>(sK + swz_off(trow, half * 4 + c));
+        const uint4 d = *reinterpret_cast<const uint4*>(sV + swz_off(trow, half * 4 + c));
+        kw[4 * c] = a.x; kw[4 * c + 1] = a.y; kw[4 * c + 2] = a.z; kw[4 * c + 3] = a.w;
+        vw[4 * c] = d.x; vw[4 * c + 1] = d.y; vw[4 * c + 2] = d.z; vw[4 * c + 3] = d.w;
+      }
+      tmem_st16(t_lane + cK + half * 16, kw);
+      tmem_st16(t_lane + cV + half * 16, vw);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(kv_tmem);
+    }
     for (int idx = 0; idx < n; ++idx) {
       const int st = idx % kBwdStages;
       const uint32_t par = idx & 1;
@@ -373,7 +404,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (warp == 0) TRACE(6, idx);
         tmem_ld32(t_lane + cS + half * 64, s0);
         tmem_ld32(t_lane + cS + half * 64 + 32, s1);
-        if (idx > 0) mbar_wait(p_empty, (idx - 1) & 1);  // dV MMA of the previous block retired: the P^T columns are free
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -448,7 +478,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       if (warp == 0) TRACE(7, idx);
-      tmem_st32(t_lane + cPT + half * 32, pp);   // (p_empty of the previous block was awaited under the S^T load)
+      tmem_st32(t_lane + cS + half * 64, pp);    // in place over this thread's own (already loaded) S^T columns
       // dP^T of this block has been in TMEM for a while: start its load while the P^T store drains
       uint32_t d0[32];
       mbar_wait(dp_full, par);

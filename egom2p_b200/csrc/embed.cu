@@ -11,6 +11,7 @@ struct EmbedParams {
   const int32_t* keep_mod;
   const int32_t* keep_pos;
   const uint8_t* pad;
+  const int32_t* row_batch;   // sample of each row, or NULL: row / budget (rows are (B, budget) slots)
   int64_t rows;
   int32_t budget;
   float* x0;
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedParams p) {
     return;
   }
   const int m = p.keep_mod[row], pos = p.keep_pos[row];
-  const int64_t b = row / p.budget;
+  const int64_t b = p.row_batch ? p.row_batch[row] : row / p.budget;
   const float4* pe = reinterpret_cast<const float4*>(p.d.pos_emb[m] + (size_t)pos * p.d.dim);
   const float4* me = reinterpret_cast<const float4*>(p.d.mod_emb[m]);
   const float4* te;
@@ -65,6 +66,7 @@ struct EmbedBwdParams {
   const int32_t* keep_mod;
   const int32_t* keep_pos;
   const uint8_t* pad;
+  const int32_t* row_batch;
   int64_t rows;
   int32_t budget;
   float* d_token_emb[EGOM2P_MAX_MODS];
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedBwdParams p) {
       if (p.d_mask_token) {
         acc_tok += g;
       } else if (p.d_token_emb[m]) {
-        const int64_t b = r / p.budget;
+        const int64_t b = p.row_batch ? p.row_batch[r] : r / p.budget;
         int64_t id = p.d.ids[m][b * p.d.len[m] + p.keep_pos[r]];
         id = id < 0 ? 0 : (id >= p.d.vocab[m] ? p.d.vocab[m] - 1 : id);
         atomicAdd(p.d_token_emb[m] + (size_t)id * D + c, g);
@@ -110,8 +112,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedBwdParams p) {
 }  // namespace egom2p
 
 extern "C" int egom2p_embed_gather_fwd(const egom2p_embed_desc* desc, const float* mask_token, const int32_t* keep_mod,
-                                       const int32_t* keep_pos, const uint8_t* pad, int64_t rows, int32_t budget,
-                                       float* x0, float* emb, void* stream) {
+                                       const int32_t* keep_pos, const uint8_t* pad, const int32_t* row_batch, int64_t rows,
+                                       int32_t budget, float* x0, float* emb, void* stream) {
   using namespace egom2p;
   EGO_REQUIRE(desc && desc->n_mods >= 1 && desc->n_mods <= EGOM2P_MAX_MODS, "embed_gather_fwd: n_mods out of range");
   EGO_REQUIRE(desc->dim > 0 && desc->dim % 4 == 0, "embed_gather_fwd: dim must be a multiple of 4");
@@ -120,20 +122,20 @@ extern "C" int egom2p_embed_gather_fwd(const egom2p_embed_desc* desc, const floa
     EGO_REQUIRE(desc->pos_emb[m] && desc->mod_emb[m], "embed_gather_fwd: modality %d tables missing", m);
     if (!mask_token) EGO_REQUIRE(desc->ids[m] && desc->token_emb[m], "embed_gather_fwd: modality %d ids/table missing", m);
   }
-  EmbedParams p{*desc, mask_token, keep_mod, keep_pos, pad, rows, budget, x0, emb};
+  EmbedParams p{*desc, mask_token, keep_mod, keep_pos, pad, row_batch, rows, budget, x0, emb};
   embed_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
   return check_launch("embed_gather_fwd");
 }
 
 extern "C" int egom2p_embed_gather_bwd(const egom2p_embed_desc* desc, const float* dx0, const float* demb,
                                        const int32_t* keep_mod, const int32_t* keep_pos, const uint8_t* pad,
-                                       int64_t rows, int32_t budget, float* const* d_token_emb,
+                                       const int32_t* row_batch, int64_t rows, int32_t budget, float* const* d_token_emb,
                                        float* const* d_mod_emb, float* d_mask_token, void* stream) {
   using namespace egom2p;
   EGO_REQUIRE(desc && desc->n_mods >= 1 && desc->n_mods <= EGOM2P_MAX_MODS, "embed_gather_bwd: n_mods out of range");
   EGO_REQUIRE(dx0 && keep_mod && keep_pos && pad && rows > 0 && budget > 0, "embed_gather_bwd: null argument");
   EmbedBwdParams p;
-  p.d = *desc; p.dx0 = dx0; p.demb = demb; p.keep_mod = keep_mod; p.keep_pos = keep_pos; p.pad = pad;
+  p.d = *desc; p.dx0 = dx0; p.demb = demb; p.keep_mod = keep_mod; p.keep_pos = keep_pos; p.pad = pad; p.row_batch = row_batch;
   p.rows = rows; p.budget = budget; p.d_mask_token = d_mask_token;
   for (int m = 0; m < EGOM2P_MAX_MODS; ++m) {
     p.d_token_emb[m] = (d_token_emb && m < desc->n_mods) ? d_token_emb[m] : nullptr;

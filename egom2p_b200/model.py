@@ -112,7 +112,7 @@ class DecoderBlock(nn.Module):
 class _Geom:
     """Shapes + key-range tables of one forward (device tensors, no host syncs)."""
     __slots__ = ("B", "N", "M", "H", "D", "enc_lo", "enc_hi", "dec_lo", "dec_hi", "x_lo", "x_hi", "eps", "m_enc", "m_dec", "m_x",
-                 "ctx_users", "dctx_acc", "epoch_ref")
+                 "ctx_users", "dctx_acc", "epoch_ref", "p_enc", "p_dec", "p_x")
 
     def build_meta(self, dev, encoder: bool = True):
         """Range metadata per attention kind, once per forward (shared by all layers, heads, fwd and bwd)."""
@@ -121,6 +121,10 @@ class _Geom:
         if self.M > 0:
             self.m_dec = ops.attn_ranges(self.B, self.M, self.M, self.dec_lo, self.dec_hi, device=dev)
             self.m_x = ops.attn_ranges(self.B, self.M, self.N, self.x_lo, self.x_hi, device=dev)
+        self.p_enc = self.p_dec = self.p_x = None
+        if ops.KernelTimer.active is not None:   # mask-aware (query, key) pair counts for the timing breakdown (device scalars)
+            cnt = lambda lo, hi: None if lo is None else (hi.long() - lo.long()).clamp(min=0).sum()
+            self.p_enc, self.p_dec, self.p_x = cnt(self.enc_lo, self.enc_hi), cnt(self.dec_lo, self.dec_hi), cnt(self.x_lo, self.x_hi)
 
 
 def _check_epoch(ref, seen):
@@ -187,23 +191,23 @@ def _mlp_bwd(dx2, x1, n2w, w13, w2, saved):
     return dx1, dx1b, dn2w, dw13, dw2
 
 
-def _self_attn_fwd(x, n1w, wqkv, wproj, B, L, H, meta, eps):
+def _self_attn_fwd(x, n1w, wqkv, wproj, B, L, H, meta, eps, pairs=None):
     D = x.shape[-1]
     h1, _, mean1, rstd1 = ops.layernorm_fwd(x, n1w, eps)
     qkv = ops.linear_fwd(h1, wqkv)
-    o, lse = ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, L, L, meta=meta)
+    o, lse = ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, L, L, meta=meta, pairs=pairs)
     x1 = ops.linear_fwd(o, wproj, addend=x, out_dtype=f32)
     return x1, (mean1, rstd1, h1, qkv, o, lse)
 
 
-def _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, saved, B, L, H, meta):
+def _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, saved, B, L, H, meta, pairs=None):
     mean1, rstd1, h1, qkv, o, lse = saved
     D = x.shape[-1]
     dwproj = ops.linear_wgrad(dx1b, o)
     do = ops.linear_dgrad(dx1b, wproj)
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, B, H, L, L, dqkv[:, :D], dqkv[:, D:2 * D],
-                 dqkv[:, 2 * D:], meta=meta)
+                 dqkv[:, 2 * D:], meta=meta, pairs=pairs)
     dwqkv = ops.linear_wgrad(dqkv, h1)
     dh1 = ops.linear_dgrad(dqkv, wqkv)
     dn1w = _zeros(n1w.numel(), x.device)
@@ -217,7 +221,7 @@ class _EncoderBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, fc3_w, wb, geom):
         wqkv, wproj, w13, w2 = wb
-        x1, sa = _self_attn_fwd(x, n1w, wqkv, wproj, geom.B, geom.N, geom.H, geom.m_enc, geom.eps)
+        x1, sa = _self_attn_fwd(x, n1w, wqkv, wproj, geom.B, geom.N, geom.H, geom.m_enc, geom.eps, geom.p_enc)
         x2, sm = _mlp_fwd(x1, n2w, w13, w2, geom.eps)
         ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
         ctx.op_epoch = geom.epoch_ref[0]
@@ -234,7 +238,7 @@ class _EncoderBlockFn(torch.autograd.Function):
         g = ctx.geom
         dx2 = dx2.contiguous()
         dx1, dx1b, dn2w, dw13, dw2 = _mlp_bwd(dx2, x1, n2w, w13, w2, sm)
-        dx, dn1w, dwqkv, dwproj = _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, sa, g.B, g.N, g.H, g.m_enc)
+        dx, dn1w, dwqkv, dwproj = _self_attn_bwd(dx1, dx1b, x, n1w, wqkv, wproj, sa, g.B, g.N, g.H, g.m_enc, g.p_enc)
         F = ctx.F
         d1, d3 = _split_w13_grad(dw13, F)
         return dx, dn1w, dwqkv, dwproj, dn2w, d1, dw2[:, :F], d3, None, None
@@ -248,12 +252,12 @@ class _DecoderBlockFn(torch.autograd.Function):
         wqkv, wsproj, wq, wkv, wxproj, w13, w2 = wb
         g = geom
         D = y.shape[-1]
-        y1, sa = _self_attn_fwd(y, n1w, wqkv, wsproj, g.B, g.M, g.H, g.m_dec, g.eps)
+        y1, sa = _self_attn_fwd(y, n1w, wqkv, wsproj, g.B, g.M, g.H, g.m_dec, g.eps, g.p_dec)
         hq, _, meanq, rstdq = ops.layernorm_fwd(y1, qnw, g.eps)
         q = ops.linear_fwd(hq, wq)
         hc, _, meanc, rstdc = ops.layernorm_fwd(context, cnw, g.eps)
         kv = ops.linear_fwd(hc, wkv)
-        o2, lse2 = ops.attn_fwd(q, kv[:, :D], kv[:, D:], g.B, g.H, g.M, g.N, meta=g.m_x)
+        o2, lse2 = ops.attn_fwd(q, kv[:, :D], kv[:, D:], g.B, g.H, g.M, g.N, meta=g.m_x, pairs=g.p_x)
         y2 = ops.linear_fwd(o2, wxproj, addend=y1, out_dtype=f32)
         y3, sm = _mlp_fwd(y2, n2w, w13, w2, g.eps)
         ctx.geom, ctx.wb, ctx.F = geom, wb, fc1_w.shape[0]
@@ -281,7 +285,7 @@ class _DecoderBlockFn(torch.autograd.Function):
         do2 = ops.linear_dgrad(dy2b, wxproj)
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
-        ops.attn_bwd(q, kv[:, :D], kv[:, D:], o2, do2, lse2, g.B, g.H, g.M, g.N, dq, dkv[:, :D], dkv[:, D:], meta=g.m_x)
+        ops.attn_bwd(q, kv[:, :D], kv[:, D:], o2, do2, lse2, g.B, g.H, g.M, g.N, dq, dkv[:, :D], dkv[:, D:], meta=g.m_x, pairs=g.p_x)
         dwq = ops.linear_wgrad(dq, hq)
         dhq = ops.linear_dgrad(dq, wq)
         dwkv = ops.linear_wgrad(dkv, hc)
@@ -304,7 +308,7 @@ class _DecoderBlockFn(torch.autograd.Function):
             else:
                 g.dctx_acc = (ctx.ctx_key, dctx)
                 dctx = None
-        dy, dn1w, dwqkv, dwsproj = _self_attn_bwd(dy1, dy1b, y, n1w, wqkv, wsproj, sa, g.B, g.M, g.H, g.m_dec)
+        dy, dn1w, dwqkv, dwsproj = _self_attn_bwd(dy1, dy1b, y, n1w, wqkv, wsproj, sa, g.B, g.M, g.H, g.m_dec, g.p_dec)
         F = ctx.F
         d1, d3 = _split_w13_grad(dw13, F)
         return (dy, dctx, dn1w, dwqkv, dwsproj, dqnw, dcnw, dwq, dwkv, dwxproj, dn2w, d1, dw2[:, :F], d3, None, None)
@@ -355,7 +359,7 @@ class _EmbedFn(torch.autograd.Function):
         ctx.plan, ctx.meta, ctx.is_decoder = plan, meta, is_decoder
         ctx.shapes = [p.shape for p in params]
         ctx.save_for_backward(*[m for m in mods])
-        R = plan.B * plan.budget
+        R = plan.rows if plan.rows is not None else plan.B * plan.budget
         if is_decoder:
             return x0.reshape(R, dim)
         return x0.reshape(R, dim), emb.reshape(R, dim)
@@ -516,6 +520,7 @@ class EgoM2P(nn.Module):
         self.static_target_rows: Optional[Dict[str, int]] = None   # {modality: valid target rows in the batch}, see forward
         self.fixed_decoder_order: Optional[List[str]] = None
         self._static_rows_dev = None
+        self.pack_rows = True   # ragged batches: run every per-row kernel over the valid tokens only (see forward)
 
     # ------------------------------------------------------------------ construction helpers (reference :179-249)
     def share_modality_embeddings(self):
@@ -788,6 +793,37 @@ class EgoM2P(nn.Module):
         """Cached bf16 operand of a modality's vocabulary head (V, D)."""
         return self._bf16(("head", mod), self.decoder_embeddings[mod].to_logits.weight)
 
+    @staticmethod
+    def _pack_plan(pl: "ops.Plan", n_valid: List[int], budget: int):
+        """Packed view of an index plan: the valid slots only (a prefix of every sample's slots), sample after sample.
+        Returns (plan over the packed rows, row offset of every sample, valid rows of every sample) -- device tensors built
+        from the host counts, no further synchronisation."""
+        dev = pl.keep_mod.device
+        B = pl.B
+        lens = torch.tensor(n_valid, dtype=torch.int32, device=dev)
+        off = torch.cumsum(lens, 0, dtype=torch.int32) - lens
+        R = int(sum(n_valid))
+        ar = torch.arange(R, dtype=torch.int32, device=dev)
+        b_of = torch.searchsorted((off + lens).contiguous(), ar, right=True).to(torch.int32)
+        slot = (b_of.long() * budget + (ar - off[b_of.long()]).long())          # flat (b, s) index of every packed row
+        pp = ops.Plan()
+        pp.B, pp.budget, pp.rows, pp.row_batch = B, budget, R, b_of.contiguous()
+        pp.keep_mod = pl.keep_mod.reshape(-1)[slot].contiguous()
+        pp.keep_pos = pl.keep_pos.reshape(-1)[slot].contiguous()
+        pp.pad = torch.zeros(R, dtype=torch.bool, device=dev)
+        pp.mod_mask = pl.mod_mask.reshape(-1)[slot]
+        pp.n_valid = pl.n_valid
+        pp.keep_idx = None
+        pp.target_ids = pp.key_lo = pp.key_hi = None
+        if pl.target_ids is not None:
+            pp.target_ids = pl.target_ids          # indexed by SLOT (the head row lists are slot lists before remapping)
+            pp.key_lo = pl.key_lo.reshape(-1)[slot]
+            pp.key_hi = pl.key_hi.reshape(-1)[slot]
+        pp.slot_index = slot
+        pp.slot_to_row = torch.full((B * budget,), -1, dtype=torch.int64, device=dev)
+        pp.slot_to_row[slot] = torch.arange(R, dtype=torch.int64, device=dev)
+        return pp, off, lens
+
     def _geom(self, B, N, M) -> _Geom:
         g = _Geom()
         g.B, g.N, g.M, g.H, g.D, g.eps = B, N, M, self.num_heads, self.dim, self.eps
@@ -838,13 +874,48 @@ class EgoM2P(nn.Module):
                             decoder=True, attn_cnt=[mod_dict[m]["decoder_attention_mask"].to(torch.int32) for m in dec_order],
                             ids=dids, causal=self.decoder_causal_mask, sep=self.decoder_sep_mask)
         N, M = ep.budget, dp.budget
-        g = self._geom(B, N, M)
-        nv = ep.n_valid
-        g.enc_lo = torch.zeros(B, N, dtype=torch.int32, device=dev)
-        g.enc_hi = nv[:, None].expand(B, N).contiguous()
-        g.x_lo = torch.zeros(B, M, dtype=torch.int32, device=dev)
-        g.x_hi = nv[:, None].expand(B, M).contiguous()
-        g.dec_lo, g.dec_hi = dp.key_lo, dp.key_hi
+        # ---- row lists of the heads, and ONE device -> host copy per forward: valid tokens per sample on both sides and the
+        # rows per head (the reference's boolean row-selects sync once per modality, egom2p_model.py:633). With
+        # `static_target_rows` set (CUDA-graph capture, egom2p_b200/graphed.py) nothing is copied.
+        row_tab, counts = ops.plan_rows(dp.mod_mask, [ids_of(m) for m in dec_mods])
+        pack = None
+        if self.static_target_rows is not None:
+            n_rows = [int(self.static_target_rows[m]) for m in dec_mods]
+            key = (tuple(n_rows), dev)
+            if self._static_rows_dev is None or self._static_rows_dev[0] != key:   # built outside graph capture (warm-up)
+                self._static_rows_dev = (key, torch.tensor(n_rows, dtype=torch.int32, device=dev))
+            torch._assert_async((counts == self._static_rows_dev[1]).all(),
+                                "egom2p_b200: static_target_rows does not match this batch")
+        else:
+            host = torch.cat([ep.n_valid, dp.n_valid, counts]).tolist()
+            ne, nd, n_rows = host[:B], host[B:2 * B], host[2 * B:]
+            # Ragged batch: PACK the rows (valid slots only, sample after sample) so that LayerNorm, every GEMM and the
+            # attention queries run over the valid tokens instead of the full budgets (the reference's masks leave ~48 % of
+            # the 2048 + 2048 slots valid on average). A sample without any encoder token keeps the
+            # slot layout: its cross-attention must average over its own pad keys.
+            if self.pack_rows and min(ne) > 0 and (sum(ne) < B * N or sum(nd) < B * M) and sum(nd) > 0:
+                pack = (ne, nd)
+        if pack is not None:
+            ep_p, e_off, e_len = self._pack_plan(ep, pack[0], N)
+            dp_p, d_off, d_len = self._pack_plan(dp, pack[1], M)
+            Re, Rd = ep_p.rows, dp_p.rows
+            g = self._geom(1, Re, Rd)        # one virtual sample: block-diagonal key ranges keep the samples apart
+            eb, db = ep_p.row_batch.long(), dp_p.row_batch.long()
+            g.enc_lo = e_off[eb].reshape(1, Re).contiguous()
+            g.enc_hi = (e_off[eb] + e_len[eb]).reshape(1, Re).contiguous()
+            g.x_lo = e_off[db].reshape(1, Rd).contiguous()
+            g.x_hi = (e_off[db] + e_len[db]).reshape(1, Rd).contiguous()
+            g.dec_lo = (dp_p.key_lo + d_off[db]).reshape(1, Rd).contiguous()
+            g.dec_hi = (dp_p.key_hi + d_off[db]).reshape(1, Rd).contiguous()
+            ep, dp = ep_p, dp_p
+        else:
+            g = self._geom(B, N, M)
+            nv = ep.n_valid
+            g.enc_lo = torch.zeros(B, N, dtype=torch.int32, device=dev)
+            g.enc_hi = nv[:, None].expand(B, N).contiguous()
+            g.x_lo = torch.zeros(B, M, dtype=torch.int32, device=dev)
+            g.x_hi = nv[:, None].expand(B, M).contiguous()
+            g.dec_lo, g.dec_hi = dp.key_lo, dp.key_hi
         g.build_meta(dev)
 
         # ---- fused embed / gather
@@ -867,28 +938,21 @@ class EgoM2P(nn.Module):
             y = self._dec_block(i, blk, y, context, g)
 
         if return_logits:
-            yn = self.decoder_norm(y).reshape(B, M, D)
+            yn = self.decoder_norm(y)
+            if pack is not None:   # back to the (B, M) slot layout the reference returns (pad slots: zeros)
+                full = torch.zeros(B * M, D, dtype=yn.dtype, device=dev)
+                full[dp.slot_index] = yn
+                yn = full
+            yn = yn.reshape(B, M, D)
             return {m: self.decoder_embeddings[m].forward_logits(yn) for m in dec_mods}
 
-        # ---- heads + loss: row lists of all modalities from ONE launch; their lengths cross to the host in one copy (the
-        # reference's boolean row-select syncs once per modality, egom2p_model.py:633). With `static_target_rows` set
-        # (CUDA-graph capture, egom2p_b200/graphed.py) the lengths are taken from the host and asserted on the device.
-        tgt_flat = dp.target_ids.reshape(-1)
-        row_tab, counts = ops.plan_rows(dp.mod_mask, [ids_of(m) for m in dec_mods])
-        if self.static_target_rows is not None:
-            n_rows = [int(self.static_target_rows[m]) for m in dec_mods]
-            key = (tuple(n_rows), dev)
-            if self._static_rows_dev is None or self._static_rows_dev[0] != key:   # built outside graph capture (warm-up)
-                self._static_rows_dev = (key, torch.tensor(n_rows, dtype=torch.int32, device=dev))
-            torch._assert_async((counts == self._static_rows_dev[1]).all(),
-                                "egom2p_b200: static_target_rows does not match this batch")
-        else:
-            n_rows = counts.tolist()
+        # ---- heads + loss (row lists from plan_rows above; in the packed layout the slot indices are remapped)
+        tgt_flat = dp.target_ids.reshape(-1)          # indexed by slot in both layouts
         rows, targets, wbs, heads = [], [], [], []
         for i, m in enumerate(dec_mods):
-            idx = row_tab[i, :n_rows[i]]
-            rows.append(idx)
+            idx = row_tab[i, :n_rows[i]]              # slots (b * M + s) of this modality's valid targets, ascending
             targets.append(tgt_flat.index_select(0, idx))
+            rows.append(dp.slot_to_row.index_select(0, idx) if pack is not None else idx)
             w = self.decoder_embeddings[m].to_logits.weight
             heads.append(w)
             wbs.append(self._bf16(("head", m), w))

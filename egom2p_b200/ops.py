@@ -46,7 +46,7 @@ class KernelTimer:
         for fam, work, unit, e0, e1 in self.records:
             d = out.setdefault(fam, {"ms": 0.0, "work": 0.0, "launches": 0, "unit": unit})
             d["ms"] += e0.elapsed_time(e1)
-            d["work"] += work
+            d["work"] += float(work)        # device scalars (mask-aware attention work) are read here, after the sync
             d["launches"] += 1
         return out
 
@@ -87,7 +87,11 @@ def _req(t: torch.Tensor, dtype, name: str):
 class Plan:
     """Outputs of egom2p_index_plan for one side (encoder or decoder)."""
     __slots__ = ("keep_idx", "keep_mod", "keep_pos", "pad", "mod_mask", "n_valid", "target_ids", "key_lo", "key_hi",
-                 "B", "budget", "order")
+                 "B", "budget", "order", "row_batch", "rows", "slot_index", "slot_to_row")
+
+    def __init__(self):
+        self.row_batch = None   # packed plans: sample of every row (int32); None: rows are the (B, budget) slots
+        self.rows = None        # packed plans: number of rows; None: B * budget
 
 
 def index_plan(masks: Sequence[torch.Tensor], mod_ids: Sequence[int], budget: int, *, decoder: bool = False,
@@ -159,26 +163,27 @@ def _embed_desc(dim, lens, vocabs, ids, tables, pos, mod):
 
 def embed_gather_fwd(plan: Plan, dim: int, lens, vocabs, ids, tables, pos, mod, mask_token=None, want_emb=True):
     lib = _lib.load()
-    rows = plan.B * plan.budget
+    packed = plan.rows is not None
+    rows = plan.rows if packed else plan.B * plan.budget
     dev = plan.keep_mod.device
-    x0 = torch.empty(plan.B, plan.budget, dim, dtype=f32, device=dev)
+    x0 = torch.empty((rows, dim) if packed else (plan.B, plan.budget, dim), dtype=f32, device=dev)
     emb = torch.empty_like(x0) if want_emb else None
     d = _embed_desc(dim, lens, vocabs, ids, tables, pos, mod)
     with _timed("embed_gather", rows * dim * 4.0 * (2 + (1 if mask_token is None else 0) + (1 if want_emb else 0)), "byte"):
         _lib.check(lib.egom2p_embed_gather_fwd(C.byref(d), _p(mask_token), _p(plan.keep_mod), _p(plan.keep_pos), _p(plan.pad),
-                                               rows, plan.budget, _p(x0), _p(emb), _s()), "embed_gather_fwd")
+                                               _p(plan.row_batch), rows, plan.budget, _p(x0), _p(emb), _s()), "embed_gather_fwd")
     return x0, emb
 
 
 def embed_gather_bwd(plan: Plan, dim: int, lens, vocabs, ids, pos, mod, dx0, demb, d_tables, d_mod, d_mask_token):
     lib = _lib.load()
-    rows = plan.B * plan.budget
+    rows = plan.rows if plan.rows is not None else plan.B * plan.budget
     d = _embed_desc(dim, lens, vocabs, ids, None, pos, mod)
     n = len(lens)
     arr_t = (C.c_void_p * _lib.MAX_MODS)(*[(_p(t) if t is not None else None) for t in (d_tables or [None] * n)])
     arr_m = (C.c_void_p * _lib.MAX_MODS)(*[(_p(t) if t is not None else None) for t in (d_mod or [None] * n)])
     _lib.check(lib.egom2p_embed_gather_bwd(C.byref(d), _p(dx0), _p(demb), _p(plan.keep_mod), _p(plan.keep_pos),
-                                           _p(plan.pad), rows, plan.budget, C.cast(arr_t, C.c_void_p),
+                                           _p(plan.pad), _p(plan.row_batch), rows, plan.budget, C.cast(arr_t, C.c_void_p),
                                            C.cast(arr_m, C.c_void_p), _p(d_mask_token), _s()), "embed_gather_bwd")
 
 
@@ -331,29 +336,30 @@ def attn_ranges(B, Mq, Nk, key_lo=None, key_hi=None, scale=None, device=None, em
     return meta
 
 
-def attn_fwd(q, k, v, B, H, Mq, Nk, key_lo=None, key_hi=None, scale=None, want_lse=True, meta=None):
-    """q (B*Mq, >=H*64) / k, v (B*Nk, ...) bf16 2-D views with unit inner stride. Returns (o (B*Mq, H*64) bf16, lse)."""
+def attn_fwd(q, k, v, B, H, Mq, Nk, key_lo=None, key_hi=None, scale=None, want_lse=True, meta=None, pairs=None):
+    """q (B*Mq, >=H*64) / k, v (B*Nk, ...) bf16 2-D views with unit inner stride. Returns (o (B*Mq, H*64) bf16, lse).
+    pairs: number of (query, key) pairs inside the ranges (host number or device scalar), for the timing breakdown only."""
     lib = _lib.load()
     if meta is None:
         meta = attn_ranges(B, Mq, Nk, key_lo, key_hi, scale, device=q.device)
     o = torch.empty(B * Mq, H * 64, dtype=bf16, device=q.device)
     lse = torch.empty(B, H, lse_stride(Mq), dtype=f32, device=q.device) if want_lse else None
     kmax = torch.empty(B * H, dtype=f32, device=q.device) if Nk > 0 else None   # scratch of the bound-path pre-pass
-    with _timed("attn_fwd", 4.0 * B * H * Mq * Nk * 64, "flop"):
+    with _timed("attn_fwd", 4.0 * H * 64 * (pairs if pairs is not None else B * Mq * Nk), "flop"):
         _lib.check(lib.egom2p_attn_fwd(_p(q), _p(k) if Nk > 0 else None, _p(v) if Nk > 0 else None, B, H, Mq, Nk, q.stride(0),
                                        k.stride(0) if Nk > 0 else 0, v.stride(0) if Nk > 0 else 0, _p(meta), _p(o),
                                        o.stride(0), _p(lse), _p(kmax), _s()), "attn_fwd")
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, B, H, Mq, Nk, dq, dk, dv, key_lo=None, key_hi=None, scale=None, meta=None):
+def attn_bwd(q, k, v, o, do, lse, B, H, Mq, Nk, dq, dk, dv, key_lo=None, key_hi=None, scale=None, meta=None, pairs=None):
     lib = _lib.load()
     scale = (64 ** -0.5) if scale is None else scale
     if meta is None:
         meta = attn_ranges(B, Mq, Nk, key_lo, key_hi, scale, device=q.device)
     assert do.stride(0) == o.stride(0)
     scratch = torch.empty(lib.egom2p_attn_bwd_scratch_bytes(B, H, Mq), dtype=torch.uint8, device=q.device)
-    with _timed("attn_bwd", 10.0 * B * H * Mq * Nk * 64, "flop"):
+    with _timed("attn_bwd", 10.0 * H * 64 * (pairs if pairs is not None else B * Mq * Nk), "flop"):
         _lib.check(lib.egom2p_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), B, H, Mq, Nk, q.stride(0), k.stride(0),
                                        v.stride(0), o.stride(0), _p(meta), scale, _p(scratch), _p(dq), _p(dk), _p(dv),
                                        dq.stride(0), dk.stride(0), dv.stride(0), _s()), "attn_bwd")

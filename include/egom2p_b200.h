@@ -76,14 +76,17 @@ typedef struct {
 } egom2p_embed_desc;
 
 /* x0[r] = tok[r] + (pos_emb[p] + mod_emb)  and  emb[r] = pos_emb[p] + mod_emb  for kept slot r; pads -> 0.
- * tok[r] = token_emb[ids] (encoder) or mask_token (decoder, mask_token != NULL). emb may be NULL. */
+ * tok[r] = token_emb[ids] (encoder) or mask_token (decoder, mask_token != NULL). emb may be NULL.
+ * row_batch: sample index of every row (int32, rows), or NULL when the rows are the (B, budget) slots in order (sample =
+ * r / budget). A non-NULL row_batch is what lets the rows of a ragged batch be PACKED (valid slots only, sample after
+ * sample), so that every per-row kernel downstream works on the valid tokens only. */
 int egom2p_embed_gather_fwd(const egom2p_embed_desc* desc, const float* mask_token, const int32_t* keep_mod,
-                            const int32_t* keep_pos, const uint8_t* pad, int64_t rows, int32_t budget, float* x0,
-                            float* emb, void* stream);
+                            const int32_t* keep_pos, const uint8_t* pad, const int32_t* row_batch, int64_t rows,
+                            int32_t budget, float* x0, float* emb, void* stream);
 /* Gradients of the above: d_token_emb[m][id] += dx0[r] (atomic scatter-add), d_mod_emb[m] += sum_r (dx0[r] + demb[r]),
  * d_mask_token += sum_r dx0[r]; all accumulate into the given fp32 buffers (any may be NULL). demb may be NULL. */
 int egom2p_embed_gather_bwd(const egom2p_embed_desc* desc, const float* dx0, const float* demb, const int32_t* keep_mod,
-                            const int32_t* keep_pos, const uint8_t* pad, int64_t rows, int32_t budget,
+                            const int32_t* keep_pos, const uint8_t* pad, const int32_t* row_batch, int64_t rows, int32_t budget,
                             float* const* d_token_emb, float* const* d_mod_emb, float* d_mask_token, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
