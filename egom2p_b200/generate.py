@@ -197,6 +197,14 @@ class GenerationSampler(nn.Module):
                                      [emb.mod_emb.detach().reshape(-1)], mask_token=m.mask_token.detach().reshape(-1), want_emb=False)
         return y0
 
+    def count_tokens(self, mod_dict):
+        """[[valid inputs per sample], [open targets per sample]] per encoder modality, as host lists (one sync)."""
+        enc_mods = [mod for mod in mod_dict if mod in self.model.encoder_embeddings]
+        B = mod_dict[enc_mods[0]]["tensor"].shape[0]
+        flat = lambda t: t.reshape(B, -1)
+        return torch.stack([torch.stack([(~flat(mod_dict[mod]["input_mask"])).sum(1), (~flat(mod_dict[mod]["target_mask"])).sum(1)])
+                            for mod in enc_mods]).tolist()
+
     @torch.no_grad()
     def forward_hidden(self, mod_dict, target: str, uncond_without: List[str], n_in: Dict[str, List[int]], pos: torch.Tensor):
         """Decoder outputs (after decoder_norm) of one decoding step for the conditional branch and -- if `uncond_without`
@@ -241,7 +249,7 @@ class GenerationSampler(nn.Module):
         return yn.reshape(nb, B * k, m.dim)
 
     @torch.no_grad()
-    def generate(self, mod_dict, schedule, top_k=0.0, top_p=0.0, text_tokenizer=None, verbose=False, seed=None):
+    def generate(self, mod_dict, schedule, top_k=0.0, top_p=0.0, text_tokenizer=None, verbose=False, seed=None, _counts=None):
         m = self.model
         info = m.modality_info
         mod_dict = {mod: {k: (v.clone() if k in ("tensor", "input_mask", "target_mask") else v) for k, v in d.items()}
@@ -251,8 +259,8 @@ class GenerationSampler(nn.Module):
         dev = mod_dict[enc_mods[0]]["tensor"].device
         flat = lambda t: t.reshape(B, -1)
         # the only device -> host transfer of the whole generation: valid input / open target counts per modality and sample
-        cnt = torch.stack([torch.stack([(~flat(mod_dict[mod]["input_mask"])).sum(1), (~flat(mod_dict[mod]["target_mask"])).sum(1)])
-                           for mod in enc_mods]).tolist()
+        # (`_counts`: supplied by GraphedGeneration, which captures this method in a CUDA graph)
+        cnt = _counts if _counts is not None else self.count_tokens(mod_dict)
         n_in = {mod: list(map(int, cnt[i][0])) for i, mod in enumerate(enc_mods)}
         n_open = {mod: int(cnt[i][1][0]) for i, mod in enumerate(enc_mods)}   # the reference assumes equal counts in a batch (:462)
 
@@ -291,3 +299,45 @@ class GenerationSampler(nn.Module):
             n_open[target] -= k
             self.stats["steps"] += 1
         return mod_dict
+
+
+class GraphedGeneration:
+    """One CUDA graph for a whole `GenerationSampler.generate` call of fixed shapes (workload, batch, schedule).
+
+    At batch 1 a guided 3-step decode is ~1100 kernel launches of a few microseconds each: issued from Python the call is
+    bound by the host (rgb -> cam: 24.6 ms per clip eager). Every shape in `generate` follows from the schedule and the
+    token counts of the initial mod_dict, so the whole call -- encoder passes, batched decoder pass, head GEMM, sampling
+    kernel and the scatter of the new tokens, for all steps -- is captured once and replayed: new conditioning tokens are
+    copied into static buffers, the generated tokens are read from static outputs. The ROAR positions and the categorical
+    draws use torch's graph-safe Philox generator (each replay draws fresh numbers); the per-step `torch.manual_seed` of the
+    eager path is not replayable and is skipped (seed=None)."""
+
+    def __init__(self, sampler: GenerationSampler, example_mod_dict, schedule, top_k=0.0, top_p=0.0, warmup: int = 2):
+        self.sampler, self.schedule, self.top_k, self.top_p = sampler, schedule, top_k, top_p
+        self.static_in = {mod: {k: v.clone() for k, v in d.items()} for mod, d in example_mod_dict.items()}
+        self.counts = sampler.count_tokens(self.static_in)
+        dev = next(iter(self.static_in.values()))["tensor"].device
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = self._run()
+        torch.cuda.synchronize(dev)
+
+    def _run(self):
+        return self.sampler.generate(self.static_in, self.schedule, top_k=self.top_k, top_p=self.top_p, seed=None, _counts=self.counts)
+
+    @torch.no_grad()
+    def __call__(self, mod_dict):
+        """mod_dict with the same shapes and the same input / target mask pattern as the example; returns the generated
+        mod_dict (static tensors, overwritten by the next call)."""
+        for mod, d in self.static_in.items():
+            for k, v in d.items():
+                v.copy_(mod_dict[mod][k], non_blocking=True)
+        self.graph.replay()
+        return self.static_out
