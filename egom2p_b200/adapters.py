@@ -135,7 +135,7 @@ class _HeadLinear(nn.Linear):
         if x2.shape[0] == 0:
             return x.new_zeros(*shape[:-1], self.weight.shape[0])
         xb = x2 if x2.dtype == torch.bfloat16 else ops.cast_bf16(x2.float().contiguous())
-        wb = ops.cast_bf16(self.weight.detach())
+        wb = ops.cached_bf16(self.weight)   # re-cast only when the master changed (ops.cached_bf16)
         return ops.linear_fwd(xb, wb, out_dtype=torch.float32).reshape(*shape[:-1], -1)
 
 

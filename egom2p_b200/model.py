@@ -54,8 +54,7 @@ class _Linear(nn.Linear):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         xb = x2 if x2.dtype == bf16 else ops.cast_bf16(x2.float().contiguous())
-        y = ops.linear_fwd(xb, ops.cast_bf16(self.weight.detach()), bias=None if self.bias is None else self.bias.detach(),
-                           out_dtype=f32)
+        y = ops.linear_fwd(xb, ops.cached_bf16(self.weight), bias=None if self.bias is None else self.bias.detach(), out_dtype=f32)
         return y.reshape(*shape[:-1], -1)
 
 
@@ -143,7 +142,7 @@ def _zeros(n, dev):
 # Bumped by every backward of the block / context / head functions below. The bf16 operand cache of EgoM2P is keyed on it:
 # weights whose gradients were just produced are about to be rewritten by an optimizer, and the fused CUDA optimizers
 # (torch._fused_adamw_) do not bump Tensor._version, so the version counter alone would leave the cache stale.
-_GRAD_GEN = [0]
+_GRAD_GEN = ops.GRAD_GEN
 
 
 def _split_w13_grad(dw13, F):

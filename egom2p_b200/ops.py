@@ -377,6 +377,29 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None):
     return out
 
 
+# Bumped by every backward of the model's autograd nodes (egom2p_b200/model.py): weights whose gradients were just produced are
+# about to be rewritten by an optimizer, and torch's fused CUDA optimizers do not bump Tensor._version.
+GRAD_GEN = [0]
+_OPERAND_CACHE: Dict[int, tuple] = {}
+
+
+def cached_bf16(weight: torch.Tensor) -> torch.Tensor:
+    """bf16 GEMM operand of a standalone weight (the sampler-facing `nn.Linear` containers: vocabulary heads,
+    decoder_proj_context), re-cast only when the master changed -- address, `_version`, or a backward since the last cast --
+    instead of on every call (a 64k x 768 head is 295 MB of traffic per cast)."""
+    w = weight.detach()
+    key = id(weight)
+    sig = (w.data_ptr(), weight._version, GRAD_GEN[0], tuple(w.shape))
+    hit = _OPERAND_CACHE.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    wb = cast_bf16(w.contiguous())
+    if len(_OPERAND_CACHE) > 64:
+        _OPERAND_CACHE.clear()
+    _OPERAND_CACHE[key] = (sig, wb)
+    return wb
+
+
 class CastPlan:
     """A fixed list of (fp32 master -> bf16 operand) casts run as ONE launch (egom2p_cast_f32_to_bf16_multi): the per-step
     refresh of the GEMM operands. items: (src (rows, cols) fp32 contiguous, dst bf16 2-D, group, slot)."""
