@@ -23,8 +23,6 @@
 //     max-exchange chain.
 //   * online path (any row of the tile with m_r > 60, or no pre-pass scratch given): the running-maximum softmax with lazy
 //     rescaling described above.
-#include <cstdlib>
-
 #include "attn_common.cuh"
 
 namespace egom2p {
@@ -165,7 +163,6 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {  // one fp32 colu
 // live in TMEM as packed bf16 pairs and enter the MMAs as TMEM operands; shared memory only carries K, V and the ones tile.
 // O accumulates in TMEM across the whole key loop (tcgen05.mma accumulate), so the math warps never wait for a PV product
 // inside the loop.
-template <int kPoly>   // kPoly > 0: every kPoly-th exponential of an interior block on the FMA pipes (ex2_poly) instead of the MUFU
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -343,15 +340,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t pk[16];
         const bool interior = rscale != 0.f && kv0 >= lo && kv0 + 32 <= hi;
         if (__all_sync(0xffffffffu, interior)) {
-          // every score of the warp's 32 x 32 patch is inside its row's range: a in [-2 m_r, 0]; one exponential in kPoly
-          // goes to the FMA pipes (the MUFU is the busiest unit of this kernel)
+          // every score of the warp's 32 x 32 patch is inside its row's range: a in [-2 m_r, 0]. (Moving a share of the
+          // exponentials to the FMA pipes with ex2_poly was measured and changed nothing: profiles/r02_attn_fwd_ncu.md.)
 #pragma unroll
-          for (int c2 = 0; c2 < 16; ++c2) {
-            const float a0 = fmaf(__uint_as_float(v[c2 * 2]), rscale, nm), a1 = fmaf(__uint_as_float(v[c2 * 2 + 1]), rscale, nm);
-            const float e0 = (kPoly > 0 && (c2 * 2) % (kPoly > 0 ? kPoly : 1) == 0) ? ex2_poly(a0) : ex2(a0);
-            const float e1 = (kPoly > 0 && (c2 * 2 + 1) % (kPoly > 0 ? kPoly : 1) == 0) ? ex2_poly(a1) : ex2(a1);
-            pk[c2] = pack_bf16(e0, e1);
-          }
+          for (int c2 = 0; c2 < 16; ++c2)
+            pk[c2] = pack_bf16(ex2(fmaf(__uint_as_float(v[c2 * 2]), rscale, nm)), ex2(fmaf(__uint_as_float(v[c2 * 2 + 1]), rscale, nm)));
         } else {
           const float sc = rscale != 0.f ? rscale : 1.f;
 #pragma unroll
@@ -532,8 +525,7 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
     tmK = tmQ;
     tmV = tmQ;
   }
-  static const int mode = [] { const char* e = getenv("EGOM2P_ATTN_FWD"); return e ? atoi(e) : 0; }();  // tuning knob: -1 online, 0 bound, n > 0 bound + poly
-  if (kmax_scratch && Nk > 0 && mode >= 0) {   // pre-pass of the bound path: max_k |k|^2 per (batch, head)
+  if (kmax_scratch && Nk > 0) {   // pre-pass of the bound path: max_k |k|^2 per (batch, head)
     EGO_REQUIRE(ldk % 8 == 0 && ((uintptr_t)K & 15) == 0, "attn_fwd: K must be 16-byte aligned with ldk %% 8 == 0");
     cudaError_t e = cudaMemsetAsync(kmax_scratch, 0, (size_t)B * H * sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("attn_fwd: memset: %s", cudaGetErrorString(e)); return EGOM2P_ERR_CUDA; }
@@ -542,15 +534,8 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
     p.kmax2 = kmax_scratch;
   }
   dim3 grid((Mq + kT - 1) / kT, H, B);
-  static std::atomic<uint64_t> attr_done[4];
-  auto launch = [&](auto kern, int slot) -> int {
-    int r = ensure_dyn_smem(kern, FwdSmem::kTotal, attr_done[slot], "attn_fwd");
-    if (r) return r;
-    kern<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-    return check_launch("attn_fwd");
-  };
-  if (mode == 3) return launch(attn_fwd_kernel<3>, 3);
-  if (mode == 4) return launch(attn_fwd_kernel<4>, 1);
-  if (mode == 8) return launch(attn_fwd_kernel<8>, 2);
-  return launch(attn_fwd_kernel<0>, 0);
+  static std::atomic<uint64_t> attr_done{0};
+  if ((rc = ensure_dyn_smem(attn_fwd_kernel, FwdSmem::kTotal, attr_done, "attn_fwd"))) return rc;
+  attn_fwd_kernel<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  return check_launch("attn_fwd");
 }
