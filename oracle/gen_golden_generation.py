@@ -5,6 +5,7 @@ UNMODIFIED reference GenerationSampler.forward_enc_dec_roar_batched (egom2p/mode
   depth_last : rgb -> depth, third ROAR step: encoder N = 5120 + 3414 = 8534 (cond) / 3414 (uncond), decoder k = 1706
   cam_first  : rgb -> cam, first step: encoder N = 5120 (cond) / 0 (uncond: the empty-context pass), decoder k = 10
   cam_second : rgb -> cam, second step: encoder N = 5130 (cond) / 10 (uncond), decoder k = 10
+  rgb_last   : depth -> rgb (BASELINE configs[4]), sixth step: encoder N = 9387 (cond) / 4267 (uncond), decoder k = 853
 
 Stores the decoder positions the reference drew, and per branch the log-sum-exp and a column slice of the logits of every
 decoder row, plus argmax / top-2 gap of the guided logits (scale 2.0). Run: `python oracle/gen_golden_generation.py` (~3 min)."""
@@ -22,7 +23,9 @@ import synth  # noqa: E402
 import gen_golden_egob as gg  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden", "generation_egob.npz")
-CASES = {"depth_last": ("tok_depth", 3414, 1706), "cam_first": ("tok_cam", 0, 10), "cam_second": ("tok_cam", 10, 10)}
+CASES = {"depth_last": ("tok_depth", 3414, 1706), "cam_first": ("tok_cam", 0, 10), "cam_second": ("tok_cam", 10, 10),
+         "rgb_last": ("tok_rgb", 4267, 853)}      # depth -> rgb, sixth ROAR step: N = 5120 + 4267 = 9387 (cond) / 4267 (uncond)
+COND = {"depth_last": "tok_rgb", "cam_first": "tok_rgb", "cam_second": "tok_rgb", "rgb_last": "tok_depth"}
 COLS = gg.COLS
 SCALE = 2.0
 
@@ -33,8 +36,8 @@ def make_state(case: str, device="cpu"):
     rng = np.random.default_rng(sum(map(ord, case)))
     L = 5120 if target in ("tok_depth", "tok_rgb") else 30
     V = 64000 if L == 5120 else 256
-    md = {"tok_rgb": {"tensor": torch.from_numpy(rng.integers(0, 64000, size=(1, 5, 32, 32), dtype=np.int64)),
-                      "input_mask": torch.zeros(1, 5120, dtype=torch.bool), "target_mask": torch.ones(1, 5120, dtype=torch.bool)}}
+    md = {COND[case]: {"tensor": torch.from_numpy(rng.integers(0, 64000, size=(1, 5, 32, 32), dtype=np.int64)),
+                       "input_mask": torch.zeros(1, 5120, dtype=torch.bool), "target_mask": torch.ones(1, 5120, dtype=torch.bool)}}
     ids = np.zeros((1, L), dtype=np.int64)
     im, tm = np.ones((1, L), dtype=bool), np.zeros((1, L), dtype=bool)
     done = rng.permutation(L)[:n_done]
@@ -59,10 +62,15 @@ def main():
     model.load_state_dict(synth.make_state_dict(gg.egob_cfg(), gg.SD_SEED), strict=True)
     sampler = GenerationSampler(model)
     res = {"cols": COLS}
+    only = sys.argv[1:]
+    if only and os.path.exists(OUT):   # add / refresh single cases without recomputing the others
+        res.update({k: v for k, v in np.load(OUT).items()})
     for case, (target, n_done, k) in CASES.items():
+        if only and case not in only:
+            continue
         md = make_state(case)
         lc, pos = sampler.forward_enc_dec_roar_batched(copy.deepcopy(md), target, k, seed=5)
-        mu = empty_img_modality(copy.deepcopy(md), "tok_rgb")
+        mu = empty_img_modality(copy.deepcopy(md), COND[case])
         lu, pos_u = sampler.forward_enc_dec_roar_batched(mu, target, k, seed=5)
         assert torch.equal(pos, pos_u)
         res[f"{case}::pos"] = pos.numpy()

@@ -1,7 +1,7 @@
 """GPU, T3 of SURVEY.md section 7: generation passes of the B200 sampler (egom2p_b200/generate.py) at the real sizes of
 BASELINE.json configs[2..3] against the UNMODIFIED reference GenerationSampler.forward_enc_dec_roar_batched in fp32
-(tests/golden/generation_egob.npz, oracle/gen_golden_generation.py): ego-b weights, encoder N in {0, 10, 3414, 5120, 5130,
-8534}, decoder k in {10, 1706}, conditional and unconditional branch batched in one decoder pass. Plus: batching ragged
+(tests/golden/generation_egob.npz, oracle/gen_golden_generation.py): ego-b weights, encoder N in {0, 10, 3414, 4267, 5120, 5130,
+8534, 9387}, decoder k in {10, 853, 1706}, conditional and unconditional branch batched in one decoder pass. Plus: batching ragged
 samples equals running them one by one, and end-to-end `generate()` invariants on a small model."""
 import os
 
@@ -38,7 +38,7 @@ def test_guided_roar_pass_matches_reference(egob_sampler, golden_dir, case):
     md = ggen.make_state(case, "cuda")
     pos = torch.from_numpy(g[f"{case}::pos"]).cuda()           # the positions the reference drew (CPU generator)
     n_in = {m: [int((~d["input_mask"]).sum())] for m, d in md.items()}
-    yn = s.forward_hidden(md, target, ["tok_rgb"], n_in, pos)   # (2, k, D): conditional, unconditional
+    yn = s.forward_hidden(md, target, [ggen.COND[case]], n_in, pos)   # (2, k, D): conditional, unconditional
     wb = s.model.head_operand(target)
     cols = torch.from_numpy(g["cols"]).cuda()
     worst = {}
