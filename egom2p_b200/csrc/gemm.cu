@@ -578,15 +578,18 @@ static int launch_gemm(const uint16_t* A, const uint16_t* B, int64_t lda, int64_
   // work units the persistent workers (CTA pairs) share: 256-row tile pairs
   const int units = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN);
   const int workers = sms / 2;
-  if (EPI == EPI_STORE && !c_bf16 && !p.bias && (!p.addend || p.addend == c_f32) && units < workers && k_blocks >= 16) {
-    // the number of splits that fills r whole rounds of workers best (r = 1..4; ties: fewer rounds = fewer reduce-adds)
-    float best = 0.f;
+  if (EPI == EPI_STORE && !c_bf16 && !p.bias && (!p.addend || p.addend == c_f32) && units < 3 * workers && k_blocks >= 16) {
+    // the number of splits that fills r whole rounds of workers best (r = 1..4; ties: fewer rounds = fewer reduce-adds).
+    // Also taken when the tiles alone already exceed one round but quantise badly (the head's dW chunks: 96 tiles on 74
+    // pairs = 65 % of two rounds; 3 splits = 288 items = 97 % of four rounds).
+    float best = (float)units / (float)(((units + workers - 1) / workers) * workers);
+    if (units < workers) best = 0.f;
     for (int r = 1; r <= 4; ++r) {
       int sp = workers * r / units;
       sp = sp < k_blocks / 8 ? sp : k_blocks / 8;
       if (sp < 1) sp = 1;
       const float util = (float)(units * sp) / (float)(((units * sp + workers - 1) / workers) * workers);
-      if (util > best + 0.02f) { best = util; splits = sp; }
+      if (util > best + (units < workers ? 0.02f : 0.10f)) { best = util; splits = sp; }
     }
     const int kb_per = (k_blocks + splits - 1) / splits;
     splits = (k_blocks + kb_per - 1) / kb_per;  // no empty splits
