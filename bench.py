@@ -516,7 +516,13 @@ def main():
         return float(ms.item())
 
     # ---- parity gate on the model about to be timed (b = 1, full size, against the unmodified reference's fp32 outputs)
-    parity = parity_gate(model, dev) if not args.no_parity else None
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_gate(model, dev)
+        except Exception as exc:  # noqa: BLE001  (reported in the line; the timing still runs)
+            parity = {"pass": False, "error": f"{type(exc).__name__}: {exc}"[:300]}
+            model.zero_grad(set_to_none=True)
 
     # ---- warm-up, then device-resident timing
     for i in range(args.warmup):
@@ -541,29 +547,34 @@ def main():
     # ---- the reference's own per-GPU batch (4): eager, and as one CUDA graph per step (egom2p_b200/graphed.py)
     batch4 = None
     if world == 1 and not args.no_batch4 and args.regime == "dense" and args.optimizer == "fused":
-        from egom2p_b200.graphed import GraphedTrainStep
-        from egom2p_b200.optim import FusedAdamW
-        nb4 = args.steps * 2
-        b4 = [{m: {k: v.to(dev) for k, v in d.items()} for m, d in make_batch(4, 777 + s, pin=False).items()} for s in range(nb4 + 1)]
-        for i in range(3):
-            step(b4[i])
-        l0 = _lib.launch_count()
-        ms4 = timed(lambda i: step(b4[i]), nb4)
-        l4 = (_lib.launch_count() - l0) / nb4
-        opt.zero_grad(set_to_none=True)
-        opt4 = FusedAdamW(groups, lr=1e-4, betas=(0.9, 0.95), eps=1e-8)
-        runner = GraphedTrainStep(model, opt4, b4[nb4], N_ENC, N_DEC, clip_grad=1.0)
-        for i in range(3):
-            runner(b4[i])
-        ms4g = timed(lambda i: runner(b4[i]), nb4)
-        model.static_target_rows = None
-        model.fixed_decoder_order = None
-        del runner, opt4
-        mk4 = lambda ms_: {"ms_per_step": ms_ / nb4, "tokens_per_s": 4 * NOMINAL_TOKENS / (ms_ / nb4 / 1e3),
-                           "mfu_vs_2250_spec": 4 * FLOP_PER_SAMPLE_STEP / (ms_ / nb4 / 1e3) / 1e12 / 2250.0}
-        batch4 = {"what": "same training step at b = 4 per GPU (the reference's batch_size), dense regime, steps = %d" % nb4,
-                  "eager": dict(mk4(ms4), launches_per_step=l4),
-                  "cuda_graph": dict(mk4(ms4g), launches_per_step=1, note="whole step (fwd + bwd + clip + AdamW) replayed as one graph")}
+        try:   # auxiliary measurement: a failure here must not cost the headline line
+            from egom2p_b200.graphed import GraphedTrainStep
+            from egom2p_b200.optim import FusedAdamW
+            nb4 = args.steps * 2
+            b4 = [{m: {k: v.to(dev) for k, v in d.items()} for m, d in make_batch(4, 777 + s, pin=False).items()} for s in range(nb4 + 1)]
+            for i in range(3):
+                step(b4[i])
+            l0 = _lib.launch_count()
+            ms4 = timed(lambda i: step(b4[i]), nb4)
+            l4 = (_lib.launch_count() - l0) / nb4
+            opt.zero_grad(set_to_none=True)
+            opt4 = FusedAdamW(groups, lr=1e-4, betas=(0.9, 0.95), eps=1e-8)
+            runner = GraphedTrainStep(model, opt4, b4[nb4], N_ENC, N_DEC, clip_grad=1.0)
+            for i in range(3):
+                runner(b4[i])
+            ms4g = timed(lambda i: runner(b4[i]), nb4)
+            model.static_target_rows = None
+            model.fixed_decoder_order = None
+            del runner, opt4
+            mk4 = lambda ms_: {"ms_per_step": ms_ / nb4, "tokens_per_s": 4 * NOMINAL_TOKENS / (ms_ / nb4 / 1e3),
+                               "mfu_vs_2250_spec": 4 * FLOP_PER_SAMPLE_STEP / (ms_ / nb4 / 1e3) / 1e12 / 2250.0}
+            batch4 = {"what": "same training step at b = 4 per GPU (the reference's batch_size), dense regime, steps = %d" % nb4,
+                      "eager": dict(mk4(ms4), launches_per_step=l4),
+                      "cuda_graph": dict(mk4(ms4g), launches_per_step=1, note="whole step (fwd + bwd + clip + AdamW) replayed as one graph")}
+        except Exception as exc:  # noqa: BLE001
+            model.static_target_rows = None
+            model.fixed_decoder_order = None
+            batch4 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- data-parallel consistency: after the timed steps every rank must hold the same weights (same all-reduced gradients,
     # same optimizer arithmetic); checked on a checksum of all parameters
@@ -626,8 +637,12 @@ def main():
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            dts = [cpu_reference_step(1, cores)[0] for _ in range(args.cpu_steps)]
-            dt = float(np.mean(dts))
+            try:
+                dts = [cpu_reference_step(1, cores)[0] for _ in range(args.cpu_steps)]
+                dt = float(np.mean(dts))
+            except Exception as exc:  # noqa: BLE001  (auxiliary measurement)
+                dt = float("nan")
+                line["cpu_baseline_error"] = f"{type(exc).__name__}: {exc}"[:300]
             line["cpu_baseline"] = {"value": NOMINAL_TOKENS / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_steps} x (1 sample = 4096 nominal tokens, fwd + bwd + clip + AdamW, fp32) of the same dense workload via oracle/egom2p_oracle.py"}
         if world == 1 and not args.no_reference_gpu:
@@ -645,6 +660,9 @@ def main():
                         res.append(ref_gpu.time_reference(rb, 20, 5, dev, make_batch))
                     except torch.cuda.OutOfMemoryError:
                         res.append({"batch_per_gpu": rb, "oom": True})
+                        torch.cuda.empty_cache()
+                    except Exception as exc:  # noqa: BLE001  (auxiliary measurement)
+                        res.append({"batch_per_gpu": rb, "error": f"{type(exc).__name__}: {exc}"[:300]})
                         torch.cuda.empty_cache()
                 line["reference_gpu"] = res
                 best = max((r["tokens_per_s"] for r in res if "tokens_per_s" in r), default=None)

@@ -1,5 +1,6 @@
-"""GPU (needs >= 2 devices, skipped otherwise): data-parallel step == single-process step on the global batch; runs
-tools/ddp_parity.py under torch.distributed.run with NCCL."""
+"""GPU: data-parallel step == single-process step on the global batch; runs tools/ddp_parity.py under
+torch.distributed.run -- with NCCL on two devices when the box has them, and always with two ranks sharing cuda:0 over gloo
+(same DistributedDataParallel reducer / bucket / hook path; the buckets travel through the host)."""
 import os
 import subprocess
 import sys
@@ -15,5 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_two_gpu_step_matches_single_process():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tools", "ddp_parity.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_two_ranks_on_one_gpu_match_single_process():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(ROOT, "tools", "ddp_parity.py"), "--one-gpu"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

@@ -17,9 +17,17 @@ from test_model_gpu import build_model
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # `--one-gpu`: both ranks on cuda:0 with the gloo backend (gradient buckets are reduced through the host, so no kernel of
+    # one rank ever waits for a kernel of the other): the same DDP code path -- reducer hooks on the per-block autograd
+    # nodes, bucketed all-reduce overlapped with backward -- on a box with a single GPU.
+    one_gpu = "--one-gpu" in sys.argv
+    local = 0 if one_gpu else local
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if one_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     cfg = synth.make_cfg(384, 6, 2, 2, ["tok_cam", "tok_depth", "tok_gaze", "tok_rgb"], video_vocab=1024, video_thw=(5, 8, 8))
     sd = synth.make_state_dict(cfg, 3)
     per = 2
