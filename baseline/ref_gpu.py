@@ -52,8 +52,9 @@ def import_reference():
     return MODALITY_INFO, create_model
 
 
-def time_reference(batch: int, steps: int, warmup: int, device: torch.device, make_batch) -> dict:
-    """ms / step of the reference training step at `batch` samples on `device`. make_batch(b, seed, pin) -> CPU mod_dict."""
+def time_reference(batch: int, steps: int, warmup: int, device: torch.device, make_batch, ddp: bool = False) -> dict:
+    """ms / step of the reference training step at `batch` samples on `device`. make_batch(b, seed, pin) -> CPU mod_dict.
+    ddp: wrap the model in DistributedDataParallel exactly as run_training_egom2p.py:514 does (process group already up)."""
     MI, create_model = import_reference()
     torch.manual_seed(0)
     model = create_model("egom2p_base_12e_12d_swiglu_nobias",
@@ -61,6 +62,9 @@ def time_reference(batch: int, steps: int, warmup: int, device: torch.device, ma
                          decoder_embeddings={m: MI[m]["decoder_embedding"]() for m in MODS},
                          modality_info={m: MI[m] for m in MODS}, num_register_tokens=0).to(device)
     model.train()
+    net = model
+    if ddp:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], find_unused_parameters=False)
     decay = [p for n, p in model.named_parameters() if not ("norm" in n or n.endswith(".bias"))]
     no_decay = [p for n, p in model.named_parameters() if ("norm" in n or n.endswith(".bias"))]
     opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}],
@@ -72,7 +76,7 @@ def time_reference(batch: int, steps: int, warmup: int, device: torch.device, ma
     def step(i):
         md = {m: dict(d) for m, d in batches[i % len(batches)].items()}   # the adapters add keys to the inner dicts
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss, _ = model(md, 2048, 2048, loss_type="mod")
+            loss, _ = net(md, 2048, 2048, loss_type="mod")
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
@@ -161,6 +165,28 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:   # torchrun: the reference under DDP, one rank per GPU (the reference's own launch mode)
+        import torch.distributed as dist
+        rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+        sys.path.insert(0, ROOT)
+        from bench import make_batch
+        res = []
+        for b in args.batch:
+            r = time_reference(b, args.steps, args.warmup, dev, lambda bb, seed, pin: make_batch(bb, seed + 1000 * rank, pin), ddp=True)
+            ms = torch.tensor([r["ms_per_step"]], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            r["ms_per_step"] = float(ms)
+            r["n_gpus"], r["tokens_per_s"] = world, world * b * 4096 / (float(ms) / 1e3)
+            res.append(r)
+        if rank == 0:
+            print(json.dumps({"reference_gpu_ddp": res}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if not available():
         print(json.dumps({"reference_gpu": None, "unavailable": "baseline/_ref/egom2p missing (run tools/install_reference.py)"}))
         return
