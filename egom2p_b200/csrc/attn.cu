@@ -82,18 +82,21 @@ __global__ void __launch_bounds__(256) attn_kmax_kernel(const uint16_t* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 256 + warp * 32;
   float best = 0.f;
+  uint4 w[8];   // all eight loads in flight before the first reduction
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int key = k0 + it * 4 + (lane >> 3);
-    float s = 0.f;
-    if (key < Nk) {
-      const uint4 w = *reinterpret_cast<const uint4*>(K + ((int64_t)b * Nk + key) * ldk + h * kD + (lane & 7) * 8);
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    w[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (key < Nk) w[it] = *reinterpret_cast<const uint4*>(K + ((int64_t)b * Nk + key) * ldk + h * kD + (lane & 7) * 8);
+  }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[u]));
-        s = fmaf(f.x, f.x, fmaf(f.y, f.y, s));
-      }
+  for (int it = 0; it < 8; ++it) {
+    const uint32_t ww[4] = {w[it].x, w[it].y, w[it].z, w[it].w};
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[u]));
+      s = fmaf(f.x, f.x, fmaf(f.y, f.y, s));
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
