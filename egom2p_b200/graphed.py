@@ -86,7 +86,6 @@ class GraphedTrainStep:
     def set_hyper(self):
         """Re-uploads lr / weight decay from optimizer.param_groups into the device table the captured kernels read (call
         after a scheduler changed them; cheap: 14 KB)."""
-        import numpy as np
         from .optim import _ITEM
         tab = self.opt._stage.numpy().view(_ITEM)
         i = 0

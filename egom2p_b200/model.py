@@ -17,7 +17,7 @@ from __future__ import annotations
 import math
 import random
 from functools import partial
-from typing import Any, Dict, List, Optional, Tuple, Union
+from typing import Any, Dict, List, Optional, Union
 
 import torch
 from torch import nn

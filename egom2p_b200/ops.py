@@ -4,7 +4,7 @@ Every function requires CUDA tensors and raises otherwise -- there is deliberate
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 

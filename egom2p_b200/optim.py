@@ -16,7 +16,6 @@ reference's scheduler code that rewrites `param_group["lr"]` / `["weight_decay"]
 the device, so the whole tail can be captured in a CUDA graph (egom2p_b200/graphed.py)."""
 from __future__ import annotations
 
-import ctypes as C
 from typing import Iterable, Optional
 
 import numpy as np
