@@ -107,12 +107,24 @@ __global__ void __launch_bounds__(256) attn_kmax_kernel(const uint16_t* __restri
   if (lane == 0) atomicMax(kmax2 + b * H + h, __float_as_int(best));
 }
 
+#ifdef EGOM2P_TRACE
+// Debug build only (EGOM2P_TRACE=1 python -m egom2p_b200.build; tools/trace_attn_fwd.py): clock stamps of one late CTA.
+__device__ long long g_fwd_trace[32];
+#define FTRACE(slot)                                                                                              \
+  do {                                                                                                            \
+    if (blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == gridDim.z - 1 && (threadIdx.x & 31) == 0) g_fwd_trace[slot] = clock64(); \
+  } while (0)
+#else
+#define FTRACE(slot) do {} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ forward
 struct AttnFwdParams {
   int B, H, Mq, Nk, S;
   RangeMeta meta;
   uint16_t* O;
   int64_t ldo;
+  int tma_out;  // the output tile leaves through one TMA store (rows past the sample's end must not exist: Mq % 128 == 0 or B == 1)
   float* lse2;  // (B, H, S), log2 domain: m + log2(l)
   const float* kmax2;  // (B, H) max_k |k|^2 (bound path), or NULL (online path only)
 };
@@ -168,7 +180,7 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {  // one fp32 colu
 // inside the loop.
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem + FwdSmem::kQ;
@@ -193,6 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int quarter = warp & 3, half = (warp >> 2) & 1;
   const int trow = quarter * 32 + lane;  // row inside the tile (== TMEM lane)
   const int row = q0 + trow;
+  if (warp == 0) FTRACE(0);   // CTA start
 
   if (warp == kTmaWarp && lane == 0) {
     mbar_init(q_full, 1);
@@ -220,6 +233,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     hi = p.meta.row_hi[(int64_t)b * p.S + row];
     rscale = p.meta.row_scale[(int64_t)b * p.S + row];
   }
+  // loaded here, not where it is used: behind the Q barrier this load's latency (~700 cycles) sat on the path to the first S
+  const float kmax2 = (p.kmax2 && warp < kAttnComputeWarps) ? p.kmax2[b * p.H + h] : 0.f;
   // key range of the whole tile = union of its two 64-row blocks (precomputed by attn_blocks_kernel over the same rows)
   const int64_t bo = (int64_t)b * (p.S / 64) + 2 * blockIdx.x;
   const int lo_cta = min(p.meta.blk_lo[bo], p.meta.blk_lo[bo + 1]), hi_cta = max(p.meta.blk_hi[bo], p.meta.blk_hi[bo + 1]);
@@ -233,6 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) FTRACE(1);   // set-up barrier passed (TMEM allocated, metadata loaded)
 
   if (warp == kTmaWarp) {
     // warp-uniform control flow (operands stay in uniform registers); one elected lane issues the copies
@@ -301,6 +317,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float m_row = 0.f;
     if (nblk > 0) {
       mbar_wait(q_full, 0);
+      if (warp == 0) FTRACE(2);   // Q landed in smem
       float q2 = 0.f;
       uint32_t qw[16];
 #pragma unroll
@@ -316,7 +333,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tmem_st16(t_lane + cQ + half * 16, qw);
       if (p.kmax2) {
-        m_row = sqrtf(q2 * p.kmax2[b * p.H + h]) * rscale;   // 0 for uniform (fully masked) and padding rows
+        m_row = sqrtf(q2 * kmax2) * rscale;   // 0 for uniform (fully masked) and padding rows
         if (m_row > kBoundLimit) *s_slow = 1;
       }
       tmem_st_wait();
@@ -327,12 +344,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     asm volatile("bar.sync 5, 256;" ::: "memory");            // the eight math warps: s_slow is final
     const bool fast = *s_slow == 0;
+    if (warp == 0) FTRACE(3);     // Q in TMEM, path decided
     if (fast) {
       for (int j = 0; j < nblk; ++j) {
         const int buf = j & 1;
         const int kv0 = lo_cta + j * kBlk + half * 32;
         mbar_wait(s_full, j & 1);   // also: PV(j-2) has retired (commit order of the single MMA thread): P buffer `buf` is free
         tc_fence_after();
+        if (warp == 0 && j == 0) FTRACE(4);          // S(0) ready
+        if (warp == 0 && j == 1) FTRACE(5);          // S(1) ready
+        if (warp == 0 && j == nblk - 1) FTRACE(6);   // S(last) ready
         uint32_t v[32];
         tmem_ld32(t_s, v);
         tmem_ld_wait();
@@ -442,10 +463,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) mbar_arrive(&p_full[buf]);
     }
     // epilogue: O / l
+    if (warp == 0) FTRACE(7);     // last P published
     uint32_t ov[32];
     if (nblk > 0) {
       mbar_wait(&pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
       tc_fence_after();
+      if (warp == 0) FTRACE(8);   // last PV retired
       tmem_ld32(t_o, ov);
       tmem_ld_wait();
     } else {
@@ -462,30 +485,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       pair_sync(quarter);
       lt = l + xs[(half ^ 1) * kT + trow];
     }
-    if (row < p.Mq) {
-      const float inv = lt > 0.f ? 1.f / lt : 0.f;
+    const float inv = lt > 0.f ? 1.f / lt : 0.f;
+    uint4 pk4[4];
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      pk4[c8].x = pack_bf16(__uint_as_float(ov[c8 * 8 + 0]) * inv, __uint_as_float(ov[c8 * 8 + 1]) * inv);
+      pk4[c8].y = pack_bf16(__uint_as_float(ov[c8 * 8 + 2]) * inv, __uint_as_float(ov[c8 * 8 + 3]) * inv);
+      pk4[c8].z = pack_bf16(__uint_as_float(ov[c8 * 8 + 4]) * inv, __uint_as_float(ov[c8 * 8 + 5]) * inv);
+      pk4[c8].w = pack_bf16(__uint_as_float(ov[c8 * 8 + 6]) * inv, __uint_as_float(ov[c8 * 8 + 7]) * inv);
+    }
+    if (p.tma_out) {
+      // The 128 x 64 bf16 tile goes through the (now idle) Q staging buffer and leaves as ONE bulk tensor store: 32 lanes
+      // writing 16 bytes each into 32 different rows cost ~1000 LSU cycles per CTA as direct global stores.
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(sQ + swz_off(trow, half * 4 + c8)) = pk4[c8];
+      fence_async_smem();
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (warp == 0 && lane == 0) {
+        tma_store_2d(&tmO, sQ, h * kD, b * p.Mq + q0);
+        tma_store_commit();
+        tma_store_wait_all();
+      }
+    } else if (row < p.Mq) {
       uint16_t* orow = p.O + ((int64_t)b * p.Mq + row) * p.ldo + h * kD + half * 32;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint4 pk;
-        pk.x = pack_bf16(__uint_as_float(ov[c8 * 8 + 0]) * inv, __uint_as_float(ov[c8 * 8 + 1]) * inv);
-        pk.y = pack_bf16(__uint_as_float(ov[c8 * 8 + 2]) * inv, __uint_as_float(ov[c8 * 8 + 3]) * inv);
-        pk.z = pack_bf16(__uint_as_float(ov[c8 * 8 + 4]) * inv, __uint_as_float(ov[c8 * 8 + 5]) * inv);
-        pk.w = pack_bf16(__uint_as_float(ov[c8 * 8 + 6]) * inv, __uint_as_float(ov[c8 * 8 + 7]) * inv);
-        reinterpret_cast<uint4*>(orow)[c8] = pk;
-      }
-      if (p.lse2 && half == 0) p.lse2[((int64_t)b * p.H + h) * p.S + row] = lt > 0.f ? m_used + log2f(lt) : INFINITY;
+      for (int c8 = 0; c8 < 4; ++c8) reinterpret_cast<uint4*>(orow)[c8] = pk4[c8];
     }
+    if (row < p.Mq && p.lse2 && half == 0) p.lse2[((int64_t)b * p.H + h) * p.S + row] = lt > 0.f ? m_used + log2f(lt) : INFINITY;
   }
+  if (warp == 0) FTRACE(9);       // outputs stored
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
   }
+  if (warp == 0) FTRACE(10);      // CTA end
 }
 
 }  // namespace egom2p
+
+#ifdef EGOM2P_TRACE
+extern "C" int egom2p_debug_attn_fwd_trace(long long* host_dst) {
+  return (int)cudaMemcpyFromSymbol(host_dst, egom2p::g_fwd_trace, sizeof(egom2p::g_fwd_trace));
+}
+#endif
 
 extern "C" int egom2p_attn_lse_stride(int32_t Mq) { return egom2p::padS(Mq); }
 extern "C" int64_t egom2p_attn_ranges_bytes(int32_t B, int32_t Mq) { return egom2p::range_meta_bytes(B, Mq); }
@@ -517,9 +561,15 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
   p.meta = carve_meta(const_cast<void*>(meta), B, Mq);
   p.O = O; p.ldo = ldo; p.lse2 = lse;
   p.kmax2 = nullptr;
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   int rc = make_tmap_bf16_2d(&tmQ, Q, (uint64_t)B * Mq, (uint64_t)H * kD, ldq, kT, kD);
   if (rc) return rc;
+  p.tma_out = ((Mq % kT == 0 || B == 1) && ((uintptr_t)O & 15) == 0 && (ldo * 2) % 16 == 0) ? 1 : 0;
+  if (p.tma_out) {
+    if ((rc = make_tmap_bf16_2d(&tmO, O, (uint64_t)B * Mq, (uint64_t)H * kD, ldo, kT, kD))) return rc;
+  } else {
+    tmO = tmQ;
+  }
   if (Nk > 0) {
     EGO_REQUIRE(K && V, "attn_fwd: K / V missing");
     if ((rc = make_tmap_bf16_2d(&tmK, K, (uint64_t)B * Nk, (uint64_t)H * kD, ldk, kBlk, kD))) return rc;
@@ -539,6 +589,6 @@ extern "C" int egom2p_attn_fwd(const uint16_t* Q, const uint16_t* K, const uint1
   dim3 grid((Mq + kT - 1) / kT, H, B);
   static std::atomic<uint64_t> attr_done{0};
   if ((rc = ensure_dyn_smem(attn_fwd_kernel, FwdSmem::kTotal, attr_done, "attn_fwd"))) return rc;
-  attn_fwd_kernel<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  attn_fwd_kernel<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmO, p);
   return check_launch("attn_fwd");
 }
