@@ -40,6 +40,7 @@ struct BwdParams {
   uint16_t* dK;
   uint16_t* dV;
   int64_t lddk, lddv;
+  int tma_out;  // dK / dV tiles leave through TMA stores (no rows past a sample's end: Nk % 128 == 0 or B == 1)
 };
 struct BwdSmem {
   static constexpr int kTile = kT * 128;  // 128 rows x 64 bf16
@@ -93,7 +94,8 @@ __device__ __forceinline__ float4 lds_f4(const void* p) {  // 16-byte shared loa
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
+                const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                const __grid_constant__ CUtensorMap tmDV, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sK = smem + BwdSmem::kK, *sV = smem + BwdSmem::kV, *sQ = smem + BwdSmem::kQ, *sDO = smem + BwdSmem::kDO,
@@ -122,8 +124,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
   const int nqb = p.S / kT;
+  if (warp == 0) TRACE(5, 63);   // CTA start
+  if (warp == kDrainWarp0 && lane == 0) {   // descriptor fetches (~1500 cycles from a cold TMA cache) off every first use
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+    tma_prefetch_desc(&tmDK);
+    tma_prefetch_desc(&tmDV);
+  }
   if (warp == kBwdTmaWarp && lane == 0) {
+    // the K / V tile does not depend on the query-block list: its load is the first thing the CTA does and overlaps the
+    // remaining barrier initialisation, the list build and the TMEM allocation
     mbar_init(kv_full, 1);
+    fence_mbar_init();
+    mbar_expect_tx(kv_full, 2 * BwdSmem::kTile);
+    tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
+    tma_load_2d(sV, &tmV, kv_full, h * kD, b * p.Nk + kv0);
     for (int i = 0; i < kBwdStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(s_full, 1);   mbar_init(s_free, kBwdMathWarps);
     mbar_init(dp_full, 1);  mbar_init(dp_free, 1);
@@ -133,10 +149,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(dkv_full, 1);
     mbar_init(kv_tmem, kBwdMathWarps);
     fence_mbar_init();
-    // the K / V tile does not depend on the query-block list: its load overlaps the list build and the TMEM allocation
-    mbar_expect_tx(kv_full, 2 * BwdSmem::kTile);
-    tma_load_2d(sK, &tmK, kv_full, h * kD, b * p.Nk + kv0);
-    tma_load_2d(sV, &tmV, kv_full, h * kD, b * p.Nk + kv0);
+    TRACE(5, 57);   // K / V loads issued
   }
   // One query block's loads (Q, dO and the five per-row metadata vectors) into ring stage st.
   auto issue_q_block = [&](int qblk, int st) {
@@ -189,13 +202,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       n += __popc(msk);
     }
     if (lane == 0) *s_n = n < kMaxQBlocks ? n : kMaxQBlocks;
+    TRACE(5, 55);   // list built
   }
-  if (warp == kBwdMmaWarp) tmem_alloc<512>(tmem_slot);
+  if (warp == kBwdMmaWarp) {
+    tmem_alloc<512>(tmem_slot);
+    TRACE(5, 54);   // TMEM allocated
+  }
+  if (warp == 1) TRACE(5, 53);   // an idle warp reaches the barrier
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n = *s_n;
+  if (warp == 0) TRACE(5, 62);   // set-up barrier passed
   // TMEM columns. P^T (bf16 pairs) is written in place over the first 32 of each thread's 64 S^T columns (k-steps 0-3 at
   // columns 0-31, 4-7 at columns 64-95, like dS^T over dP^T), which frees 64 columns for K and V as packed bf16: the S^T and
   // dP^T products read their A operand from TMEM instead of shared memory (-32 KB of the 272 KB of shared-memory traffic per
@@ -357,7 +376,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (warp == kDrainWarp0) TRACE(12, idx);
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_read();   // the boxes have left shared memory; the reduces complete on their own (kernel boundary)
   } else {
     // -------------------------------------------------------------------------------------------- math warps
     const int quarter = warp & 3, half = warp >> 2;  // half: which 64 of the block's 128 queries (TMEM columns)
@@ -368,6 +387,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float SC = p.scale_log2, RN = p.scale_log2 * kLn2;
     if (n > 0) {   // K, V: smem -> TMEM (this thread's key row, its half of the head dim = 16 packed columns each)
       mbar_wait(kv_full, 0);
+      if (warp == 0) TRACE(5, 56);   // K / V landed
       uint32_t kw[16], vw[16];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -382,6 +402,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(kv_tmem);
+      if (warp == 0) TRACE(5, 58);   // K / V in TMEM
     }
     for (int idx = 0; idx < n; ++idx) {
       const int st = idx % kBwdStages;
@@ -539,6 +560,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(dkv_full, 0);
       tc_fence_after();
     }
+    if (warp == 0) TRACE(5, 61);   // dK / dV complete in TMEM
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       uint32_t v[32];
@@ -549,23 +571,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] = 0u;
       }
-      if (kidx < p.Nk) {
+      uint4 pk[4];
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        pk[c8].x = pack_bf16(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
+        pk[c8].y = pack_bf16(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
+        pk[c8].z = pack_bf16(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
+        pk[c8].w = pack_bf16(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
+      }
+      if (p.tma_out) {
+        // staged in the (idle) first Q / dO ring stages as swizzled 128 x 64 tiles and written by one TMA store each below:
+        // 32 lanes storing 16 bytes into 32 different rows cost ~1000 cycles per CTA that nothing overlaps at one CTA per SM
+        uint8_t* stage = which == 0 ? sQ : sDO;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(stage + swz_off(trow, half * 4 + c8)) = pk[c8];
+        if (warp == 0) TRACE(5, 52 - which);
+      } else if (kidx < p.Nk) {
         uint16_t* out = (which == 0 ? p.dV + ((int64_t)b * p.Nk + kidx) * p.lddv : p.dK + ((int64_t)b * p.Nk + kidx) * p.lddk) +
                         h * kD + half * 32;
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
-          pk.y = pack_bf16(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
-          pk.z = pack_bf16(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
-          pk.w = pack_bf16(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
-          reinterpret_cast<uint4*>(out)[c8] = pk;
-        }
+        for (int c8 = 0; c8 < 4; ++c8) reinterpret_cast<uint4*>(out)[c8] = pk[c8];
       }
     }
+    if (p.tma_out) {
+      fence_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight math warps
+      if (warp == 0) TRACE(5, 50);
+      if (warp == 0 && lane == 0) {
+        tma_store_2d(&tmDV, sQ, h * kD, b * p.Nk + kv0);
+        tma_store_2d(&tmDK, sDO, h * kD, b * p.Nk + kv0);
+        tma_store_commit();
+        tma_store_wait_read();   // the tiles have left shared memory; the writes complete on their own
+      }
+    }
+    if (warp == 0) TRACE(5, 60);   // dK / dV written
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) TRACE(5, 59);     // CTA end
   if (warp == kBwdMmaWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -665,14 +708,22 @@ extern "C" int egom2p_attn_bwd(const uint16_t* Q, const uint16_t* K, const uint1
     EGO_REQUIRE(lddk % 8 == 0 && lddv % 8 == 0 && ((uintptr_t)dK & 15) == 0 && ((uintptr_t)dV & 15) == 0, "attn_bwd: dK/dV alignment");
     static std::atomic<uint64_t> attr_done{0};
     if ((rc = ensure_dyn_smem(attn_bwd_kernel, BwdSmem::kTotal, attr_done, "attn_bwd"))) return rc;
-    CUtensorMap tmQ, tmDO, tmK, tmV, tmDQ;
+    CUtensorMap tmQ, tmDO, tmK, tmV, tmDQ, tmDK, tmDV;
     if ((rc = make_tmap_bf16_2d(&tmQ, Q, (uint64_t)B * Mq, (uint64_t)H * kD, ldq, kT, kD))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmDO, dO, (uint64_t)B * Mq, (uint64_t)H * kD, ldo, kT, kD))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmK, K, (uint64_t)B * Nk, (uint64_t)H * kD, ldk, kT, kD))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmV, V, (uint64_t)B * Nk, (uint64_t)H * kD, ldv, kT, kD))) return rc;
     if ((rc = make_tmap_2d(&tmDQ, dq_acc, 4, (uint64_t)B * Mq, (uint64_t)H * kD, (uint64_t)H * kD, 32, 32))) return rc;
-    BwdParams pb{B, H, Mq, Nk, S, rm, lse, ndelta, scale * kLog2e, dK, dV, lddk, lddv};
-    attn_bwd_kernel<<<dim3((Nk + kT - 1) / kT, H, B), kBwdThreads, BwdSmem::kTotal, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, pb);
+    const int tma_out = (Nk % kT == 0 || B == 1) ? 1 : 0;
+    if (tma_out) {
+      if ((rc = make_tmap_bf16_2d(&tmDK, dK, (uint64_t)B * Nk, (uint64_t)H * kD, lddk, kT, kD))) return rc;
+      if ((rc = make_tmap_bf16_2d(&tmDV, dV, (uint64_t)B * Nk, (uint64_t)H * kD, lddv, kT, kD))) return rc;
+    } else {
+      tmDK = tmK;
+      tmDV = tmV;
+    }
+    BwdParams pb{B, H, Mq, Nk, S, rm, lse, ndelta, scale * kLog2e, dK, dV, lddk, lddv, tma_out};
+    attn_bwd_kernel<<<dim3((Nk + kT - 1) / kT, H, B), kBwdThreads, BwdSmem::kTotal, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, tmDK, tmDV, pb);
     if ((rc = check_launch("attn_bwd"))) return rc;
   }
   const int64_t rows = (int64_t)B * Mq;

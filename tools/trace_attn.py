@@ -21,3 +21,9 @@ t0 = buf[5 * 64]
 for idx in range(16):
     ev = sorted((buf[s * 64 + idx] - t0, names[s]) for s in range(16) if buf[s * 64 + idx])
     print("it %2d: " % idx + "  ".join("%s@%d" % (n, t) for t, n in ev))
+
+g = lambda i: buf[5 * 64 + i] - buf[5 * 64 + 63]
+print("epilogue: dV staged %d | dK staged %d | all warps staged %d" % (g(52), g(51), g(50)))
+print("before the barrier: K/V loads issued %d | list built %d | TMEM allocated %d | idle warp at barrier %d | K/V landed %d" % (g(57), g(55), g(54), g(53), g(56)))
+print("fixed costs (cycles from CTA start): set-up barrier %d | K/V in TMEM %d | first S^T ready %d | ... | last dS stored %d | dK/dV complete %d | written %d | CTA end %d"
+      % (g(62), g(58), buf[6 * 64] - buf[5 * 64 + 63], buf[10 * 64 + 15] - buf[5 * 64 + 63], g(61), g(60), g(59)))
