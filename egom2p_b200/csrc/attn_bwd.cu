@@ -58,7 +58,7 @@ static_assert(BwdSmem::kTotal <= 232448, "attention backward exceeds the 227 KB 
 __device__ long long g_trace[16 * 64];
 #define TRACE(slot, idx)                                                                          \
   do {                                                                                            \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 64 && (threadIdx.x & 31) == 0) \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z - 1 && (idx) < 64 && (threadIdx.x & 31) == 0) \
       g_trace[(slot) * 64 + (idx)] = clock64();                                                   \
   } while (0)
 #else
