@@ -29,7 +29,8 @@ def _ref(q, k, v, do, lo, hi, H):
 
 
 @pytest.mark.parametrize("B,H,Mq,Nk,mode", [(1, 1, 128, 128, "full"), (2, 3, 200, 200, "prefix"), (2, 2, 300, 517, "prefix"),
-                                            (2, 2, 260, 260, "segments"), (1, 1, 20, 24, "prefix"), (1, 12, 2048, 2048, "segments")])
+                                            (2, 2, 260, 260, "segments"), (1, 1, 20, 24, "prefix"), (1, 12, 2048, 2048, "segments"),
+                                            (2, 2, 256, 384, "prefix")])   # B > 1 with whole tiles: the TMA-store epilogue
 def test_attention_bwd(ops, B, H, Mq, Nk, mode):
     gen = torch.Generator().manual_seed(Mq * 5 + Nk)
     D = H * 64

@@ -283,7 +283,8 @@ def _attn_ref(q, k, v, lo, hi, H):
 
 @pytest.mark.parametrize("gain", [1.0, 3.0])   # 1: |q| max|k| scale log2e ~ 15 -> bound-path softmax; 3: ~ 140 -> online-maximum path
 @pytest.mark.parametrize("B,H,Mq,Nk,mode", [(2, 3, 200, 200, "prefix"), (1, 2, 128, 64, "full"), (2, 4, 300, 517, "prefix"),
-                                            (2, 2, 260, 260, "segments"), (1, 1, 20, 24, "prefix"), (1, 12, 2048, 2048, "segments")])
+                                            (2, 2, 260, 260, "segments"), (1, 1, 20, 24, "prefix"), (1, 12, 2048, 2048, "segments"),
+                                            (2, 2, 256, 384, "prefix")])   # B > 1 with whole tiles: the TMA-store epilogue
 def test_attention_fwd(ops, B, H, Mq, Nk, mode, gain):
     gen = torch.Generator().manual_seed(Mq * 7 + Nk)
     D = H * 64
