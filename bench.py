@@ -679,7 +679,7 @@ def main():
                                               round(d["work"] / (d["ms"] / 1e3 + 1e-12) / (1e12 if d["unit"] == "flop" else 1e9), 1)}
                                       for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}},
         }
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:   # rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             try:
                 res = [cpu_reference_arm(1, cores) for _ in range(args.cpu_steps)]
