@@ -11,11 +11,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/egom2p"
 DST = os.path.join(ROOT, "baseline", "_ref", "egom2p")
 
+def install(force: bool = True) -> int:
+    """Copies the package; returns the number of files under baseline/_ref/egom2p (0 if the reference tree is absent)."""
+    if not os.path.isdir(SRC):
+        return 0
+    if os.path.isdir(DST):
+        if not force:
+            return sum(len(f) for _, _, f in os.walk(DST))
+        shutil.rmtree(DST)
+    shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    return sum(len(f) for _, _, f in os.walk(DST))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(SRC):
         sys.exit(f"{SRC} not found (the reference tree exists in the authoring container only)")
-    if os.path.isdir(DST):
-        shutil.rmtree(DST)
-    shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
-    n = sum(len(f) for _, _, f in os.walk(DST))
-    print(f"copied {n} files to {DST}")
+    print(f"copied {install()} files to {DST}")
